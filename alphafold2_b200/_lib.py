@@ -1,0 +1,76 @@
+"""ctypes binding of libaf2b200.so (include/af2b200.h).  No torch extension, no pybind: the C ABI is the
+drop-in boundary.  There is deliberately NO fallback: if the library is missing or the device is not
+sm_100, every op raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libaf2b200.so")
+
+_lib = None
+
+vp, ll, ci, cf = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+
+class FFWeights(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("bn", ci)]
+
+
+class AttnWeights(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_qkv", vp), ("w_gate", vp), ("b_gate", vp),
+                ("w_out", vp), ("b_out", vp), ("w_edge", vp)]
+
+
+class TriMulWeights(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_left", vp), ("b_left", vp), ("w_right", vp),
+                ("b_right", vp), ("w_ogate", vp), ("b_ogate", vp), ("on_gamma", vp), ("on_beta", vp),
+                ("w_out", vp), ("b_out", vp), ("bn", ci)]
+
+
+class OuterWeights(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_lr", vp), ("b_lr", vp), ("w_out", vp), ("b_out", vp)]
+
+
+_SIGNATURES = {
+    "af2_last_error": (C.c_char_p, []),
+    "af2_abi_version": (ci, []),
+    "af2_check_device": (ci, []),
+    "af2_feed_forward": (ci, [C.POINTER(FFWeights), vp, ll, ci, ci, vp, ll, vp]),
+    "af2_feed_forward_workspace": (ll, [ll, ci, ci]),
+    "af2_axial_attention": (ci, [C.POINTER(AttnWeights), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_axial_attention_workspace": (ll, [ci, ci, ci, ci, ci, ci, ci]),
+    "af2_triangle_multiply": (ci, [C.POINTER(TriMulWeights), vp, vp, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_triangle_multiply_workspace": (ll, [ci, ci, ci]),
+    "af2_outer_mean": (ci, [C.POINTER(OuterWeights), vp, vp, vp, ci, ci, ci, ci, cf, vp, ll, vp]),
+    "af2_outer_mean_workspace": (ll, [ci, ci, ci, ci]),
+    "af2_rotary": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "af2_layernorm_bf16": (ci, [vp, vp, vp, vp, ll, ci, cf, vp]),
+    "af2_gemm_bf16_f32": (ci, [vp, ll, ll, vp, ll, ll, vp, ll, ll, ci, ci, ci, ci, ci, vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). alphafold2_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        msg = load().af2_last_error().decode("utf-8", "replace")
+        if code == -1:
+            raise ValueError(f"af2b200: {msg}")
+        raise RuntimeError(f"af2b200 (code {code}): {msg}")

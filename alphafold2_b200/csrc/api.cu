@@ -1,0 +1,584 @@
+// Host side of libaf2b200.so: TMA descriptor construction, kernel launches and the per-module
+// orchestration behind the C ABI declared in include/af2b200.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/af2b200.h"
+#include "attention_tc.cuh"
+#include "gemm_tc.cuh"
+#include "simt_kernels.cuh"
+
+using namespace af2;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(AF2_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define AF2_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != AF2_OK) return _r; \
+  } while (0)
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map. dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
+int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+              const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
+  auto fn = encode_fn();
+  if (!fn) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail(AF2_ERR_BAD_ARG, "TMA base pointer not 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] & 15) return fail(AF2_ERR_BAD_ARG, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gstr[i]);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AF2_OK;
+}
+
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  long long size, off;
+  bool ok;
+  Arena(void* b, long long s) : base(static_cast<char*>(b)), size(s), off(0), ok(true) {}
+  template <class T>
+  T* take(long long count) {
+    long long bytes = align_up(count * (long long)sizeof(T), 256);
+    if (off + bytes > size) {
+      ok = false;
+      return nullptr;
+    }
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// GEMM launch
+// -------------------------------------------------------------------------------------------------
+struct GemmCall {
+  const void* A; long long lda; long long a_batch;
+  const void* Bm; long long ldb; long long b_batch;
+  int M, N, K, batch;
+  bool mn_major;
+  int bn;                 // 64 / 128 / 256
+  // epilogue
+  int mode, act, layout, use_rowscale;
+  void* out; long long ld_out; long long out_batch;
+  const float* bias; const float* rowscale; const float* resid; long long ld_resid;
+  int cm_inner, cm_pitch;
+  int out_cols;           // 0: N (N/2 for GATED); else explicit number of valid output columns
+};
+
+template <int BN, int STAGES, bool MN>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, STAGES, MN>;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const long long total = (long long)p.batch * m_tiles * p.num_ntiles;
+  if (total <= 0) return AF2_OK;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  kern<<<grid, 256, L::TOTAL, s>>>(ta, tb, p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+int launch_gemm(const GemmCall& c, cudaStream_t s) {
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0 || c.batch <= 0) return AF2_OK;
+  CUtensorMap ta, tb;
+  const int BN = c.bn;
+  if (!c.mn_major) {
+    unsigned long long da[3] = {(unsigned long long)c.K, (unsigned long long)c.M, (unsigned long long)c.batch};
+    unsigned long long sa[2] = {(unsigned long long)c.lda * 2, (unsigned long long)(c.batch > 1 ? c.a_batch : c.lda * c.M) * 2};
+    unsigned ba[3] = {64, 128, 1};
+    AF2_TRY(make_tmap(&ta, c.A, 3, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B));
+    unsigned long long db[3] = {(unsigned long long)c.K, (unsigned long long)c.N, (unsigned long long)c.batch};
+    unsigned long long sb[2] = {(unsigned long long)c.ldb * 2, (unsigned long long)(c.batch > 1 && c.b_batch ? c.b_batch : c.ldb * c.N) * 2};
+    unsigned bb[3] = {64, (unsigned)BN, 1};
+    AF2_TRY(make_tmap(&tb, c.Bm, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    unsigned long long da[3] = {(unsigned long long)c.M, (unsigned long long)c.K, (unsigned long long)c.batch};
+    unsigned long long sa[2] = {(unsigned long long)c.lda * 2, (unsigned long long)(c.batch > 1 ? c.a_batch : c.lda * c.K) * 2};
+    unsigned bx[3] = {64, 64, 1};
+    AF2_TRY(make_tmap(&ta, c.A, 3, da, sa, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+    unsigned long long db[3] = {(unsigned long long)c.N, (unsigned long long)c.K, (unsigned long long)c.batch};
+    unsigned long long sb[2] = {(unsigned long long)c.ldb * 2, (unsigned long long)(c.batch > 1 ? c.b_batch : c.ldb * c.K) * 2};
+    AF2_TRY(make_tmap(&tb, c.Bm, 3, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = c.M; p.N = c.N; p.K = c.K; p.batch = c.batch;
+  p.num_ntiles = (c.N + BN - 1) / BN;
+  p.out_cols = c.out_cols > 0 ? c.out_cols : ((c.mode == EPI_GATED_BF16) ? c.N / 2 : c.N);
+  p.rowscale = c.rowscale; p.resid = c.resid; p.ld_resid = c.ld_resid;
+  p.out_batch_stride = c.out_batch;
+  p.cm_inner = c.cm_inner > 0 ? c.cm_inner : 1; p.cm_pitch = c.cm_pitch > 0 ? c.cm_pitch : 1;
+  p.tile.mode = c.mode; p.tile.act = c.act; p.tile.layout = c.layout; p.tile.use_rowscale = c.use_rowscale;
+  p.tile.out = c.out; p.tile.bias = c.bias; p.tile.ld = c.ld_out;
+  if (c.mn_major) {
+    if (BN == 256) return launch_gemm_inst<256, 4, true>(ta, tb, p, s);
+    if (BN == 128) return launch_gemm_inst<128, 6, true>(ta, tb, p, s);
+    return launch_gemm_inst<64, 8, true>(ta, tb, p, s);
+  }
+  if (BN == 256) return launch_gemm_inst<256, 4, false>(ta, tb, p, s);
+  if (BN == 128) return launch_gemm_inst<128, 6, false>(ta, tb, p, s);
+  return launch_gemm_inst<64, 8, false>(ta, tb, p, s);
+}
+
+int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+GemmCall linear_call(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K) {
+  GemmCall c;
+  memset(&c, 0, sizeof(c));
+  c.A = A; c.lda = lda; c.Bm = W; c.ldb = ldw; c.M = M; c.N = N; c.K = K; c.batch = 1;
+  c.mn_major = false; c.bn = pick_bn(N);
+  return c;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LayerNorm launch
+// -------------------------------------------------------------------------------------------------
+int launch_layernorm(const LnParams& p, cudaStream_t s) {
+  if (p.T <= 0) return AF2_OK;
+  if (p.d % 4 != 0 || p.d > 1024) return fail(AF2_ERR_BAD_ARG, "LayerNorm: dim %d must be a multiple of 4 and <= 1024", p.d);
+  const long long blocks_needed = (p.T + 7) / 8;
+  const long long cap = (long long)sm_count() * 16;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  if (p.d <= 128) layernorm_rows_kernel<1><<<grid, 256, 0, s>>>(p);
+  else if (p.d <= 256) layernorm_rows_kernel<2><<<grid, 256, 0, s>>>(p);
+  else if (p.d <= 512) layernorm_rows_kernel<4><<<grid, 256, 0, s>>>(p);
+  else layernorm_rows_kernel<8><<<grid, 256, 0, s>>>(p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
+  const size_t smem = (size_t)p.d * 33 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(chan_to_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((p.n + 31) / 32, p.rows);
+  chan_to_token_kernel<<<grid, 256, smem, s>>>(p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// attention launch (one folded batch group)
+// -------------------------------------------------------------------------------------------------
+template <int DH>
+int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
+                          const AttnParams& p, cudaStream_t s) {
+  using L = AttnSmem<DH>;
+  static bool configured = false;
+  auto kern = attention_tc_kernel<DH>;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((p.n + 127) / 128, p.heads, p.nbatch);
+  kern<<<grid, 192, L::TOTAL, s>>>(tq, tk, tv, tbias, p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+// qkv: bf16 [tokens, 3I] (q | k | v), token(b', i) = b' * tok_sb + i * tok_si
+int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nbatch, long long tok_sb, long long tok_si,
+                     const __nv_bfloat16* bias, int npad, const uint8_t* mask, const __nv_bfloat16* gate,
+                     __nv_bfloat16* out, cudaStream_t s) {
+  const long long I = (long long)heads * dh;
+  const long long ld = 3 * I;
+  CUtensorMap tq, tk, tv, tb;
+  unsigned long long dims[4] = {(unsigned long long)dh, (unsigned long long)n, (unsigned long long)heads, (unsigned long long)nbatch};
+  unsigned long long str[3] = {(unsigned long long)(tok_si * ld * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * ld * 2)};
+  unsigned box[4] = {(unsigned)dh, 128, 1, 1};
+  const CUtensorMapSwizzle swz = (dh == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz));
+  AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz));
+  AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz));
+  if (bias) {
+    unsigned long long bd[3] = {(unsigned long long)npad, (unsigned long long)n, (unsigned long long)heads};
+    unsigned long long bs[2] = {(unsigned long long)npad * 2, (unsigned long long)n * npad * 2};
+    unsigned bb[3] = {64, 128, 1};
+    AF2_TRY(make_tmap(&tb, bias, 3, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    tb = tq;
+  }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.heads = heads; p.nbatch = nbatch; p.has_bias = bias != nullptr;
+  p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
+  p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
+  if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, p, s);
+  if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, p, s);
+  return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
+}
+
+int ew_grid(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* af2_last_error(void) { return g_err; }
+int af2_abi_version(void) { return 1; }
+
+int af2_check_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(AF2_ERR_UNSUPPORTED_DEVICE, "libaf2b200 is built for sm_100a only; device has compute capability %d.x", major);
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+long long af2_feed_forward_workspace(long long tokens, int d, int hidden) {
+  return align_up(tokens * d * 2, 256) + align_up(tokens * hidden * 2, 256) + 1024;
+}
+
+int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d, int hidden, void* workspace,
+                     long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x) return fail(AF2_ERR_BAD_ARG, "feed_forward: null argument");
+  if (d % 8 || hidden % 8) return fail(AF2_ERR_BAD_ARG, "feed_forward: d=%d and hidden=%d must be multiples of 8", d, hidden);
+  if (tokens > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "feed_forward: too many tokens");
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* xn = ar.take<__nv_bfloat16>(tokens * d);
+  __nv_bfloat16* hbuf = ar.take<__nv_bfloat16>(tokens * hidden);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "feed_forward: workspace too small");
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
+  AF2_TRY(launch_layernorm(lp, s));
+  // h = a * gelu(g)
+  const int half = w->bn / 2;
+  const int n1p = (hidden + half - 1) / half * w->bn;   // packed accumulator columns
+  GemmCall c1 = linear_call(xn, d, w->w1, d, (int)tokens, n1p, d);
+  c1.bn = w->bn; c1.mode = EPI_GATED_BF16; c1.act = ACT_GELU; c1.layout = LAYOUT_TOKEN;
+  c1.out = hbuf; c1.ld_out = hidden; c1.bias = w->b1; c1.out_cols = hidden;
+  AF2_TRY(launch_gemm(c1, s));
+  GemmCall c2 = linear_call(hbuf, hidden, w->w2, hidden, (int)tokens, d, hidden);
+  c2.mode = EPI_RESID_F32; c2.out = x; c2.ld_out = d; c2.bias = w->b2; c2.resid = x; c2.ld_resid = d;
+  AF2_TRY(launch_gemm(c2, s));
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads, int dim_head, int row_attn) {
+  const long long T = (long long)B * h * wdim, I = (long long)heads * dim_head;
+  const int n = row_attn ? wdim : h;
+  const long long npad = align_up(n, 8);
+  return align_up(T * d * 2, 256) + align_up(T * 3 * I * 2, 256) + 2 * align_up(T * I * 2, 256) +
+         align_up((long long)B * heads * n * npad * 2, 256) + 1024;
+}
+
+int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask, int B,
+                        int h, int wdim, int d, int heads, int dim_head, int row_attn, void* workspace,
+                        long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x) return fail(AF2_ERR_BAD_ARG, "axial_attention: null argument");
+  if (dim_head != 32 && dim_head != 64) return fail(AF2_ERR_BAD_ARG, "axial_attention: dim_head %d unsupported (32 or 64)", dim_head);
+  if (d % 8) return fail(AF2_ERR_BAD_ARG, "axial_attention: dim %d must be a multiple of 8", d);
+  const long long T = (long long)B * h * wdim, I = (long long)heads * dim_head;
+  if (T > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "axial_attention: too many tokens");
+  const int n = row_attn ? wdim : h;
+  const int nb = row_attn ? h : wdim;
+  const int npad = (int)align_up(n, 8);
+  const bool has_bias = edges != nullptr && w->w_edge != nullptr;
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* xn = ar.take<__nv_bfloat16>(T * d);
+  __nv_bfloat16* qkv = ar.take<__nv_bfloat16>(T * 3 * I);
+  __nv_bfloat16* gate = ar.take<__nv_bfloat16>(T * I);
+  __nv_bfloat16* og = ar.take<__nv_bfloat16>(T * I);
+  __nv_bfloat16* bias = ar.take<__nv_bfloat16>((long long)B * heads * n * npad);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "axial_attention: workspace too small");
+
+  // 1. LayerNorm (+ pair bias from the RAW edges; fused when the edges are x itself)
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
+  const bool fuse_bias = has_bias && edges == x && B == 1;
+  // pad key columns are loaded by TMA next to valid ones: keep them finite (zero)
+  if (has_bias && npad != n) CUDA_OK(cudaMemsetAsync(bias, 0, (size_t)B * heads * n * npad * 2, s));
+  if (fuse_bias) {
+    lp.wb = w->w_edge; lp.bias_out = bias; lp.heads = heads; lp.bias_hs = (long long)n * npad; lp.n_inner = n; lp.pitch = npad;
+  }
+  AF2_TRY(launch_layernorm(lp, s));
+  if (has_bias && !fuse_bias) {
+    for (int b = 0; b < B; ++b) {
+      LnParams bp;
+      memset(&bp, 0, sizeof(bp));
+      bp.x = edges + (long long)b * n * n * d; bp.T = (long long)n * n; bp.d = d; bp.eps = 1e-5f;
+      bp.wb = w->w_edge; bp.bias_out = bias + (long long)b * heads * n * npad; bp.heads = heads;
+      bp.bias_hs = (long long)n * npad; bp.n_inner = n; bp.pitch = npad;
+      AF2_TRY(launch_layernorm(bp, s));
+    }
+  }
+  // 2. projections
+  GemmCall cq = linear_call(xn, d, w->w_qkv, d, (int)T, (int)(3 * I), d);
+  cq.mode = EPI_STORE_BF16; cq.layout = LAYOUT_TOKEN; cq.out = qkv; cq.ld_out = 3 * I;
+  AF2_TRY(launch_gemm(cq, s));
+  GemmCall cg = linear_call(xn, d, w->w_gate, d, (int)T, (int)I, d);
+  cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = I; cg.bias = w->b_gate;
+  AF2_TRY(launch_gemm(cg, s));
+  // 3. attention per batch element
+  const long long tok_sb = row_attn ? wdim : 1, tok_si = row_attn ? 1 : wdim;
+  for (int b = 0; b < B; ++b) {
+    const long long t0 = (long long)b * h * wdim;
+    AF2_TRY(launch_attention(qkv + t0 * 3 * I, heads, dim_head, n, nb, tok_sb, tok_si,
+                             has_bias ? bias + (long long)b * heads * n * npad : nullptr, npad,
+                             mask ? mask + t0 : nullptr, gate + t0 * I, og + t0 * I, s));
+  }
+  // 4. to_out + bias + residual
+  GemmCall co = linear_call(og, I, w->w_out, I, (int)T, d, (int)I);
+  co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
+  AF2_TRY(launch_gemm(co, s));
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+long long af2_triangle_multiply_workspace(int B, int N, int d) {
+  const long long T = (long long)B * N * N;
+  const long long np8 = align_up(N, 8), np4 = align_up(N, 4);
+  return 3 * align_up(T * d * 2, 256)                               // xn, gate, tn
+         + 2 * align_up((long long)d * B * N * np8 * 2, 256)          // Lc, Rc
+         + align_up((long long)d * B * N * np4 * 4, 256)              // Oc
+         + align_up(T * 4, 256) + 1024;                               // mask as float
+}
+
+int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned char* mask, int B, int N, int d,
+                          int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x) return fail(AF2_ERR_BAD_ARG, "triangle_multiply: null argument");
+  if (d % 32) return fail(AF2_ERR_BAD_ARG, "triangle_multiply: dim %d must be a multiple of 32", d);
+  const long long T = (long long)B * N * N;
+  if (T > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "triangle_multiply: too many tokens");
+  const int np8 = (int)align_up(N, 8), np4 = (int)align_up(N, 4);
+  const long long cs_lr = (long long)B * N * np8;   // channel stride of Lc / Rc
+  const long long cs_o = (long long)B * N * np4;    // channel stride of Oc
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* xn = ar.take<__nv_bfloat16>(T * d);
+  __nv_bfloat16* gate = ar.take<__nv_bfloat16>(T * d);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(T * d);
+  __nv_bfloat16* Lc = ar.take<__nv_bfloat16>(d * cs_lr);
+  __nv_bfloat16* Rc = ar.take<__nv_bfloat16>(d * cs_lr);
+  float* Oc = ar.take<float>(d * cs_o);
+  float* maskf = ar.take<float>(T);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_multiply: workspace too small");
+
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
+  AF2_TRY(launch_layernorm(lp, s));
+  if (mask) {
+    mask_to_float_kernel<<<ew_grid(T), 256, 0, s>>>(mask, maskf, T);
+    CUDA_OK(cudaGetLastError());
+  }
+  if (np8 != N) {   // pad columns of the channel-major operands are read by TMA as K / MN padding: keep them zero
+    CUDA_OK(cudaMemsetAsync(Lc, 0, (size_t)d * cs_lr * 2, s));
+    CUDA_OK(cudaMemsetAsync(Rc, 0, (size_t)d * cs_lr * 2, s));
+  }
+  // left / right: (proj + b) * mask * sigmoid(gate + b)  -> channel-major [c][b*N + i][k]
+  const int half = w->bn / 2;
+  const int npk = (d + half - 1) / half * w->bn;
+  for (int side = 0; side < 2; ++side) {
+    GemmCall c = linear_call(xn, d, side ? w->w_right : w->w_left, d, (int)T, npk, d);
+    c.bn = w->bn; c.mode = EPI_GATED_BF16; c.act = ACT_SIGMOID; c.layout = LAYOUT_CHANNEL;
+    c.out = side ? Rc : Lc; c.ld_out = cs_lr; c.bias = side ? w->b_right : w->b_left;
+    c.use_rowscale = mask != nullptr; c.rowscale = maskf; c.cm_inner = N; c.cm_pitch = np8; c.out_cols = d;
+    AF2_TRY(launch_gemm(c, s));
+  }
+  GemmCall cg = linear_call(xn, d, w->w_ogate, d, (int)T, d, d);
+  cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = d; cg.bias = w->b_ogate;
+  AF2_TRY(launch_gemm(cg, s));
+  // per-channel contraction, batch = channels
+  for (int b = 0; b < B; ++b) {
+    GemmCall c;
+    memset(&c, 0, sizeof(c));
+    const long long boff = (long long)b * N * np8;
+    if (!ingoing) {   // O_c = L_c R_c^T : both K-major (k contiguous)
+      c.A = Lc + boff; c.Bm = Rc + boff; c.mn_major = false;
+    } else {          // O_c[i][j] = sum_k R_c[k][i] L_c[k][j] : both MN-major
+      c.A = Rc + boff; c.Bm = Lc + boff; c.mn_major = true;
+    }
+    c.lda = np8; c.ldb = np8; c.a_batch = cs_lr; c.b_batch = cs_lr;
+    c.M = N; c.N = N; c.K = N; c.batch = d; c.bn = pick_bn(N);
+    c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = Oc + (long long)b * N * np4; c.ld_out = np4; c.out_batch = cs_o;
+    AF2_TRY(launch_gemm(c, s));
+  }
+  // LN over channels * out_gate -> token-major bf16
+  ChanLnParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = B * N; cp.n = N; cp.d = d; cp.mode = 0;
+  cp.gamma = w->on_gamma; cp.beta = w->on_beta; cp.gate = gate; cp.eps = 1e-5f; cp.y = tn;
+  AF2_TRY(launch_chan_to_token(cp, s));
+  GemmCall co = linear_call(tn, d, w->w_out, d, (int)T, d, d);
+  co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
+  AF2_TRY(launch_gemm(co, s));
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+long long af2_outer_mean_workspace(int B, int S, int N, int d) {
+  const long long Tm = (long long)B * S * N, Tx = (long long)B * N * N;
+  const long long np8 = align_up(N, 8), np4 = align_up(N, 4);
+  return align_up(Tm * d * 2, 256) + align_up((long long)2 * d * B * S * np8 * 2, 256) +
+         align_up((long long)d * B * N * np4 * 4, 256) + align_up(Tx * d * 2, 256) + align_up(Tm * 4, 256) +
+         align_up(Tx * 4, 256) + 1024;
+}
+
+int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
+                   int N, int d, float eps, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x || !m) return fail(AF2_ERR_BAD_ARG, "outer_mean: null argument");
+  if (d % 32) return fail(AF2_ERR_BAD_ARG, "outer_mean: dim %d must be a multiple of 32", d);
+  const long long Tm = (long long)B * S * N, Tx = (long long)B * N * N;
+  if (Tm > 0x7fffffffLL || Tx > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "outer_mean: too many tokens");
+  const int np8 = (int)align_up(N, 8), np4 = (int)align_up(N, 4);
+  const long long cs_lr = (long long)B * S * np8, cs_o = (long long)B * N * np4;
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* mn = ar.take<__nv_bfloat16>(Tm * d);
+  __nv_bfloat16* LRc = ar.take<__nv_bfloat16>(2LL * d * cs_lr);
+  float* Oc = ar.take<float>(d * cs_o);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Tx * d);
+  float* maskf = ar.take<float>(Tm);
+  float* scale = ar.take<float>(Tx);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_mean: workspace too small");
+
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = m; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = mn; lp.T = Tm; lp.d = d; lp.eps = 1e-5f;
+  AF2_TRY(launch_layernorm(lp, s));
+  if (msa_mask) {
+    mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm);
+    CUDA_OK(cudaGetLastError());
+    outer_scale_kernel<<<ew_grid(Tx), 256, 0, s>>>(msa_mask, scale, B, S, N, eps);
+    CUDA_OK(cudaGetLastError());
+  }
+  if (np8 != N) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * cs_lr * 2, s));
+  // [left | right] = (LN(m) W^T + b) * mask  -> channel-major [c][b*S + s][i]
+  GemmCall c = linear_call(mn, d, w->w_lr, d, (int)Tm, 2 * d, d);
+  c.mode = EPI_STORE_BF16; c.layout = LAYOUT_CHANNEL; c.out = LRc; c.ld_out = cs_lr; c.bias = w->b_lr;
+  c.use_rowscale = msa_mask != nullptr; c.rowscale = maskf; c.cm_inner = N; c.cm_pitch = np8;
+  AF2_TRY(launch_gemm(c, s));
+  // O_c[i][j] = sum_s L_c[s][i] R_c[s][j]  (MN-major operands, K = S)
+  for (int b = 0; b < B; ++b) {
+    GemmCall g;
+    memset(&g, 0, sizeof(g));
+    g.A = LRc + (long long)b * S * np8; g.Bm = LRc + (long long)d * cs_lr + (long long)b * S * np8;
+    g.mn_major = true; g.lda = np8; g.ldb = np8; g.a_batch = cs_lr; g.b_batch = cs_lr;
+    g.M = N; g.N = N; g.K = S; g.batch = d; g.bn = pick_bn(N);
+    g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)b * N * np4; g.ld_out = np4; g.out_batch = cs_o;
+    AF2_TRY(launch_gemm(g, s));
+  }
+  ChanLnParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = B * N; cp.n = N; cp.d = d; cp.mode = 1;
+  cp.scale = msa_mask ? scale : nullptr; cp.scale_const = 1.0f / (float)S; cp.y = tn;
+  AF2_TRY(launch_chan_to_token(cp, s));
+  GemmCall co = linear_call(tn, d, w->w_out, d, (int)Tx, d, d);
+  co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
+  AF2_TRY(launch_gemm(co, s));
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int af2_rotary(const float* x, const float* sin_, const float* cos_, float* y, int b, int h, int n, int dh, int rot,
+               int sincos_batch, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dh % 2 || rot % 2 || rot > dh) return fail(AF2_ERR_BAD_ARG, "rotary: dh=%d rot=%d must be even, rot <= dh", dh, rot);
+  const long long pairs = (long long)b * h * n * (dh / 2);
+  if (pairs == 0) return AF2_OK;
+  rotary_kernel<<<ew_grid(pairs), 256, 0, s>>>(x, sin_, cos_, y, b, h, n, dh, rot, sincos_batch);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+int af2_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y_bf16, long long T, int d,
+                       float eps, af2_stream_t stream) {
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.gamma = gamma; lp.beta = beta; lp.y = static_cast<__nv_bfloat16*>(y_bf16); lp.T = T; lp.d = d; lp.eps = eps;
+  return launch_layernorm(lp, static_cast<cudaStream_t>(stream));
+}
+
+int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const void* Bm, long long ldb, long long b_batch,
+                      float* C, long long ldc, long long c_batch, int M, int N, int K, int batch, int mn_major,
+                      af2_stream_t stream) {
+  GemmCall c;
+  memset(&c, 0, sizeof(c));
+  c.A = A; c.lda = lda; c.a_batch = a_batch; c.Bm = Bm; c.ldb = ldb; c.b_batch = b_batch;
+  c.M = M; c.N = N; c.K = K; c.batch = batch; c.mn_major = mn_major != 0; c.bn = pick_bn(N);
+  c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = C; c.ld_out = ldc; c.out_batch = c_batch;
+  return launch_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

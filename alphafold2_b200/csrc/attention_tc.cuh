@@ -1,0 +1,312 @@
+// Axial self-attention with shared additive pair bias and the reference's two-sided mask, on tcgen05.
+// Replaces Attention.forward (alphafold2.py:125-190) as driven by AxialAttention (alphafold2.py:219-255).
+//
+// One CTA = one (folded batch element b', head h, block of 128 queries).  Keys/values are streamed in
+// blocks of 128 through a 2-stage TMA pipeline together with the matching [128 q x 128 k] bf16 bias tile.
+//   S_j = Q K_j^T           tcgen05.mma  (M=128, N=128, K=DH)  -> TMEM (double buffered, 2 x 128 cols)
+//   softmax warps (4)       TMEM -> regs, + bias + mask, online max/sum, P_j -> smem (bf16, 128B swizzle),
+//                           rescale O in TMEM when the running max moves
+//   O  += P_j V_j           tcgen05.mma  (M=128, N=DH, K=128), V consumed MN-major straight from its
+//                           [key][dh] layout
+//   epilogue                O / l * sigmoid-gate -> bf16 [token, h*DH + e]
+//
+// Mask semantics (quirk Q1): logits where !(mask[q] & mask[k]) are REPLACED by -FLT_MAX.  For an unmasked
+// query that gives probability exactly 0 on masked keys; for a masked query every logit is equal, i.e. a
+// uniform distribution over all n keys (masked ones included).  Keys >= n (tile padding) never count.
+#pragma once
+#include "common.cuh"
+
+namespace af2 {
+
+struct AttnParams {
+  int n;              // sequence length along the attended axis
+  int heads;
+  int nbatch;         // folded batch B'
+  int has_bias;
+  const uint8_t* mask;        // nullptr or bool mask; element (b', i) at mask[b'*mask_sb + i*mask_si]
+  long long mask_sb, mask_si;
+  const __nv_bfloat16* gate;  // sigmoid(gating) [token, heads*DH]; token(b', i) = b'*tok_sb + i*tok_si
+  __nv_bfloat16* out;         // [token, heads*DH]
+  long long tok_sb, tok_si;
+  long long ld_gate, ld_out;
+};
+
+template <int DH>
+struct AttnSmem {
+  static constexpr int Q_BYTES = 128 * DH * 2;
+  static constexpr int K_BYTES = 128 * DH * 2;
+  static constexpr int V_BYTES = 128 * DH * 2;
+  static constexpr int BIAS_BYTES = 128 * 128 * 2;      // two 64-key boxes of [128 q rows x 128 B]
+  static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BIAS_BYTES;
+  static constexpr int P_BYTES = 128 * 128 * 2;         // two 64-key K-chunks of [128 q rows x 128 B]
+  static constexpr int Q_OFF = 0;
+  static constexpr int STAGE_OFF = Q_BYTES;
+  static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
+  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr int KB_OFF = BAR_OFF + 128;          // float key bias (0 / -inf), one per key of the current block pair
+  static constexpr int TOTAL = KB_OFF + 2 * 128 * 4 + 1024;
+};
+
+// tmQ/tmK/tmV: 4-D maps over the projection buffer, dims (e [DH], i [n], h [heads], b' [nbatch]),
+// box (DH, 128, 1, 1), swizzle = DH*2 bytes.  tmBias: 3-D (k [npad], q [n], h), box (64, 128, 1), SW128.
+template <int DH>
+__global__ void __launch_bounds__(192, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
+                    const __grid_constant__ AttnParams p) {
+  using L = AttnSmem<DH>;
+  constexpr uint32_t SWZ = (DH == 64) ? SWZ_128 : SWZ_64;
+  constexpr uint32_t ROWB = DH * 2;                 // bytes per Q/K/V row
+  constexpr uint32_t SBO = 8 * ROWB;                // 8-row swizzle atom
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2]
+  uint64_t* s_empty = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * 128;
+  const int nkv = (p.n + 127) / 128;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t S_COL = 0, O_COL = 256;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    if (p.has_bias) prefetch_tmap(&tmBias);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      tma_load_4d(smem + L::Q_OFF, &tmQ, q_full, 0, q0, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        uint8_t* sk = smem + L::STAGE_OFF + st * L::STAGE_BYTES;
+        uint8_t* sv = sk + L::K_BYTES;
+        uint8_t* sbias = sv + L::V_BYTES;
+        mbar_arrive_expect_tx(&kv_full[st], L::K_BYTES + L::V_BYTES + (p.has_bias ? L::BIAS_BYTES : 0));
+        tma_load_4d(sk, &tmK, &kv_full[st], 0, j * 128, h, b);
+        tma_load_4d(sv, &tmV, &kv_full[st], 0, j * 128, h, b);
+        if (p.has_bias) {
+          tma_load_3d(sbias, &tmBias, &kv_full[st], j * 128, q0, h);
+          tma_load_3d(sbias + 16384, &tmBias, &kv_full[st], j * 128 + 64, q0, h);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, V is MN-major
+    const uint32_t sq = smem_u32(smem + L::Q_OFF);
+    const uint32_t sp = smem_u32(smem + L::P_OFF);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sk = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint64_t ad = umma_smem_desc(sq + k * 32, 16, SBO, SWZ);
+          const uint64_t bd = umma_smem_desc(sk + k * 32, 16, SBO, SWZ);
+          umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      if (j + 1 < nkv) issue_s(j + 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A = P: two 64-key chunks of 16 KB, K step 32 B inside a chunk
+          const uint64_t ad = umma_smem_desc(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128);
+          // B = V [key][dh], MN-major: 16 keys = 2 swizzle atoms of 8 key-rows
+          const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
+          umma_bf16(tmem_base + O_COL, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ softmax + epilogue (warps 2..5) ==============
+    const int q = warp & 3;
+    const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
+    const int qi = q0 + r;
+    const bool q_in = qi < p.n;
+    bool q_valid = true;
+    if (p.mask && q_in) q_valid = p.mask[b * p.mask_sb + qi * p.mask_si] != 0;
+    const int sm_tid = threadIdx.x - 64;  // 0..127
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float NEG_INF = -__int_as_float(0x7f800000);
+
+    float m_run = NEG_INF, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      // per-key additive term for this block (0 = usable key, -inf = masked or beyond n); slot st is safe to
+      // rewrite: its previous readers (block j-2) passed the named barrier of block j-1 before we got here.
+      {
+        const int kidx = j * 128 + sm_tid;
+        float kb = NEG_INF;
+        if (kidx < p.n) kb = (!p.mask || p.mask[b * p.mask_sb + kidx * p.mask_si]) ? 0.f : NEG_INF;
+        keyb[st * 128 + sm_tid] = kb;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+
+      float s[128];
+      {
+        uint32_t u[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(tmem_base + S_COL + st * 128 + c * 32 + lane_sel, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+
+      // logits (log2 domain) = (s + bias) * log2e + keyterm
+      const uint8_t* sbias = smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES + L::V_BYTES;
+      const float* kbs = keyb + st * 128;
+      float mx = NEG_INF;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {        // 16 chunks of 8 keys
+        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (p.has_bias) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(sbias + (c >> 3) * 16384 + swz128_off(r, c & 7));
+          bv[0] = bf16lo_to_f32(raw.x); bv[1] = bf16hi_to_f32(raw.x);
+          bv[2] = bf16lo_to_f32(raw.y); bv[3] = bf16hi_to_f32(raw.y);
+          bv[4] = bf16lo_to_f32(raw.z); bv[5] = bf16hi_to_f32(raw.z);
+          bv[6] = bf16lo_to_f32(raw.w); bv[7] = bf16hi_to_f32(raw.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = c * 8 + i;
+          const float kb = kbs[k];
+          const bool in_range = (j * 128 + k) < p.n;
+          float v = q_valid ? ((s[k] + bv[i]) * LOG2E + kb) : (in_range ? 0.f : NEG_INF);
+          s[k] = v;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
+      const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
+      float lsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 128; ++k) {
+        const float e = fast_exp2(s[k] - m_use);
+        s[k] = e;
+        lsum += e;
+      }
+      l_run = l_run * corr + lsum;
+      m_run = m_new;
+
+      // previous P V must be complete before O is rescaled and before P smem is overwritten
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          tmem_ld32(tmem_base + O_COL + c * 32 + lane_sel, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          tmem_st32(tmem_base + O_COL + c * 32 + lane_sel, o);
+        }
+        tmem_st_wait();
+      }
+      // P_j -> smem, bf16, K-major 128B swizzle (two 64-key chunks)
+      uint8_t* spb = smem + L::P_OFF;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        uint4 pk = make_uint4(pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]), pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]),
+                              pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]), pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
+        *reinterpret_cast<uint4*>(spb + (c >> 3) * 16384 + swz128_off(r, c & 7)) = pk;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l * gate -> out ----
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
+    const __nv_bfloat16* gp = p.gate + tok * p.ld_gate + h * DH;
+    __nv_bfloat16* op = p.out + tok * p.ld_out + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_base + O_COL + c * 32 + lane_sel, o);
+      tmem_ld_wait();
+      if (q_in) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint4 g = *reinterpret_cast<const uint4*>(gp + c * 32 + i);
+          const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float a = __uint_as_float(o[i + 2 * t]) * inv_l * bf16lo_to_f32(gw[t]);
+            const float bb = __uint_as_float(o[i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
+            ow[t] = pack_bf16x2(a, bb);
+          }
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace af2

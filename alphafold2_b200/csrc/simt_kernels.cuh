@@ -1,0 +1,213 @@
+// Bandwidth-bound helper kernels (no tensor-core work): row LayerNorm with optional fused pair-bias
+// projection, channel-major -> token-major LayerNorm*gate, pair-mask counts, rotary embedding.
+// All are coalesced / vectorised and sized as grid-stride loops over 148 x k CTAs.
+#pragma once
+#include "common.cuh"
+
+namespace af2 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = LayerNorm(x) * gamma + beta  -> bf16 [T, d]          (nn.LayerNorm, eps inside sqrt)
+// optionally  bias[h][(t / n_inner) * pitch + t % n_inner] = <x_raw[t, :], Wb[h, :]>   (bf16)
+//   (edges_to_attn_bias of alphafold2.py:214-217,245-247 acts on the RAW, un-normalised pair tensor)
+// One warp per row; the row lives in registers (d <= 1024, d % 4 == 0).
+// ------------------------------------------------------------------------------------------------
+struct LnParams {
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;        // may be nullptr (bias only)
+  long long T;
+  int d;
+  float eps;
+  const float* wb;         // [H, d] or nullptr
+  __nv_bfloat16* bias_out; // [H][bias_hs]
+  int heads;
+  long long bias_hs;       // elements between heads
+  int n_inner, pitch;      // token t -> (t / n_inner) * pitch + t % n_inner
+};
+
+template <int MAXC>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * warps_per_block;
+  const int nchunk = p.d >> 2;   // float4 chunks per row
+  for (long long t = warp_global; t < p.T; t += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(p.x + t * p.d);
+    float4 v[MAXC];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int idx = lane + 32 * c;
+      if (idx < nchunk) {
+        v[c] = __ldg(xr + idx);
+        sum += v[c].x + v[c].y + v[c].z + v[c].w;
+      } else {
+        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mean = warp_sum(sum) / p.d;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int idx = lane + 32 * c;
+      if (idx < nchunk) {
+        const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, dd = v[c].w - mean;
+        sq += a * a + b * b + cc * cc + dd * dd;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / p.d + p.eps);
+    if (p.y) {
+      uint2* yr = reinterpret_cast<uint2*>(p.y + t * p.d);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int idx = lane + 32 * c;
+        if (idx < nchunk) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + idx);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + idx);
+          const float o0 = (v[c].x - mean) * rstd * g.x + b.x;
+          const float o1 = (v[c].y - mean) * rstd * g.y + b.y;
+          const float o2 = (v[c].z - mean) * rstd * g.z + b.z;
+          const float o3 = (v[c].w - mean) * rstd * g.w + b.w;
+          yr[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        }
+      }
+    }
+    if (p.wb) {
+      const long long off = (t / p.n_inner) * p.pitch + (t % p.n_inner);
+      for (int h = 0; h < p.heads; ++h) {
+        const float4* wr = reinterpret_cast<const float4*>(p.wb + static_cast<long long>(h) * p.d);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const int idx = lane + 32 * c;
+          if (idx < nchunk) {
+            const float4 w = __ldg(wr + idx);
+            acc += v[c].x * w.x + v[c].y * w.y + v[c].z * w.z + v[c].w * w.w;
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) p.bias_out[h * p.bias_hs + off] = __float2bfloat16(acc);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel-major fp32 contraction output  ->  token-major bf16 operand of the following Linear.
+//   src[c][row * pitch + j]   (c < d channels, row < rows, j < n)    token = row * n + j
+//   mode 0 (triangle multiply tail, alphafold2.py:315-316):  y = LayerNorm_c(src) * gamma + beta, * gate[token, c]
+//   mode 1 (outer mean tail,      alphafold2.py:347-349):    y = src * scale[token]
+// Block = 256 threads handles 32 consecutive j of one row: coalesced reads along j, smem transpose,
+// coalesced bf16 writes along c.
+// ------------------------------------------------------------------------------------------------
+struct ChanLnParams {
+  const float* src;
+  long long chan_stride;
+  int pitch, rows, n, d;
+  int mode;
+  const float* gamma;
+  const float* beta;
+  const __nv_bfloat16* gate;   // [tokens, d]
+  const float* scale;          // [tokens]
+  float scale_const;           // used when scale == nullptr (mode 1)
+  float eps;
+  __nv_bfloat16* y;            // [tokens, d]
+};
+
+__global__ void __launch_bounds__(256) chan_to_token_kernel(const ChanLnParams p) {
+  extern __shared__ float tile[];   // [d][33]
+  const int jt = blockIdx.x, row = blockIdx.y;
+  const int j0 = jt * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool j_ok = (j0 + lane) < p.n;
+  const float* src = p.src + static_cast<long long>(row) * p.pitch + j0 + lane;
+  for (int c = warp; c < p.d; c += 8)
+    tile[c * 33 + lane] = j_ok ? __ldg(src + c * p.chan_stride) : 0.f;
+  __syncthreads();
+  for (int tk = warp; tk < 32; tk += 8) {
+    if (j0 + tk >= p.n) break;
+    const long long token = static_cast<long long>(row) * p.n + j0 + tk;
+    if (p.mode == 0) {
+      float sum = 0.f;
+      for (int c = lane; c < p.d; c += 32) sum += tile[c * 33 + tk];
+      const float mean = warp_sum(sum) / p.d;
+      float sq = 0.f;
+      for (int c = lane; c < p.d; c += 32) {
+        const float a = tile[c * 33 + tk] - mean;
+        sq += a * a;
+      }
+      const float rstd = rsqrtf(warp_sum(sq) / p.d + p.eps);
+      for (int c = lane; c < p.d; c += 32) {
+        const float g = __bfloat162float(p.gate[token * p.d + c]);
+        const float o = ((tile[c * 33 + tk] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c)) * g;
+        p.y[token * p.d + c] = __float2bfloat16(o);
+      }
+    } else {
+      const float sc = p.scale ? __ldg(p.scale + token) : p.scale_const;
+      for (int c = lane; c < p.d; c += 32) p.y[token * p.d + c] = __float2bfloat16(tile[c * 33 + tk] * sc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// OuterMean normaliser (quirk Q3, alphafold2.py:345-347):
+//   scale[b][i][j] = 1 / (S * (sum_s mask[b,s,i] * mask[b,s,j] + eps))      (fp32, like the reference)
+// ------------------------------------------------------------------------------------------------
+__global__ void outer_scale_kernel(const uint8_t* __restrict__ mask, float* __restrict__ scale, int B, int S, int N,
+                                   float eps) {
+  const long long total = static_cast<long long>(B) * N * N;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = idx % N;
+    const int i = (idx / N) % N;
+    const int b = idx / (static_cast<long long>(N) * N);
+    const uint8_t* mb = mask + static_cast<long long>(b) * S * N;
+    int cnt = 0;
+    for (int s = 0; s < S; ++s) cnt += (mb[s * N + i] != 0) & (mb[s * N + j] != 0);
+    scale[idx] = 1.0f / (static_cast<float>(S) * (static_cast<float>(cnt) + eps));
+  }
+}
+
+// bool mask -> float 0/1 row scale
+__global__ void mask_to_float_kernel(const uint8_t* __restrict__ mask, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = mask[i] ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply_rotary_pos_emb (rotary.py:9-20): x [b, h, n, dh] fp32; sin/cos [bs, n, rot] (bs = 1 or b).
+// Interleaved pairs (x0, x1) -> (x0 c0 - x1 s0, x1 c1 + x0 s1); channels >= rot pass through.
+// ------------------------------------------------------------------------------------------------
+__global__ void rotary_kernel(const float* __restrict__ x, const float* __restrict__ sn, const float* __restrict__ cs,
+                              float* __restrict__ y, int b, int h, int n, int dh, int rot, int sincos_batch) {
+  const long long pairs = static_cast<long long>(b) * h * n * (dh / 2);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < pairs;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pr = idx % (dh / 2);
+    const long long row = idx / (dh / 2);      // (b, h, n) flattened
+    const int ni = row % n;
+    const int bi = row / (static_cast<long long>(n) * h);
+    const float2 v = reinterpret_cast<const float2*>(x)[idx];
+    float2 o = v;
+    if (2 * pr + 1 < rot) {
+      const long long so = (static_cast<long long>(sincos_batch > 1 ? bi : 0) * n + ni) * rot + 2 * pr;
+      const float s0 = sn[so], s1 = sn[so + 1], c0 = cs[so], c1 = cs[so + 1];
+      // separate roundings (no FMA contraction) so the result is bit-identical to x*cos + rot(x)*sin
+      o.x = __fadd_rn(__fmul_rn(v.x, c0), __fmul_rn(-v.y, s0));
+      o.y = __fadd_rn(__fmul_rn(v.y, c1), __fmul_rn(v.x, s1));
+    }
+    reinterpret_cast<float2*>(y)[idx] = o;
+  }
+}
+
+}  // namespace af2

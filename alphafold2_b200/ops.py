@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C ABI: argument validation, weight packing, workspace management.
+
+PyTorch is used for device memory and streams only; every FLOP of the hot path runs inside libaf2b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+_WORKSPACE: Dict[torch.device, torch.Tensor] = {}
+_DEVICE_CHECKED = set()
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (alphafold2_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    dev = t.device
+    if dev not in _DEVICE_CHECKED:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().af2_check_device())
+        _DEVICE_CHECKED.add(dev)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer, reused by every op (ops on one stream are serialised)."""
+    device = torch.device(device)
+    buf = _WORKSPACE.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WORKSPACE.pop(device, None)
+        buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACE[device] = buf
+    return buf
+
+
+def _mask_u8(mask: Optional[torch.Tensor], shape, name: str) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if mask.dtype != torch.bool:
+        mask = mask.bool()
+    if tuple(mask.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(mask.shape)}")
+    return mask.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing (done once per parameter version; see alphafold2.py::_PackedCache)
+# --------------------------------------------------------------------------------------------------
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def gated_half(n_out: int) -> int:
+    return 128 if n_out >= 128 else (64 if n_out >= 64 else 32)
+
+
+def pack_gated(w_val, b_val, w_gate, b_gate, half: int):
+    """Interleave value/gate rows per accumulator column tile: [half value rows | half gate rows] * tiles."""
+    n_out, k = w_val.shape
+    tiles = (n_out + half - 1) // half
+    w = torch.zeros(tiles * 2 * half, k, dtype=torch.float32, device=w_val.device)
+    b = torch.zeros(tiles * 2 * half, dtype=torch.float32, device=w_val.device)
+    for t in range(tiles):
+        lo, hi = t * half, min(n_out, (t + 1) * half)
+        w[t * 2 * half: t * 2 * half + (hi - lo)] = w_val[lo:hi]
+        w[t * 2 * half + half: t * 2 * half + half + (hi - lo)] = w_gate[lo:hi]
+        b[t * 2 * half: t * 2 * half + (hi - lo)] = b_val[lo:hi]
+        b[t * 2 * half + half: t * 2 * half + half + (hi - lo)] = b_gate[lo:hi]
+    return _bf16(w), b.contiguous()
+
+
+class Packed:
+    """Keeps the packed tensors alive next to the ctypes struct that points at them."""
+
+    def __init__(self, struct, tensors):
+        self.struct = struct
+        self.tensors = tensors
+
+
+def pack_feed_forward(norm_w, norm_b, w1, b1, w2, b2) -> Packed:
+    hidden = w2.shape[1]
+    half = gated_half(hidden)
+    a_w, g_w = w1[:hidden].detach().float(), w1[hidden:].detach().float()
+    a_b, g_b = b1[:hidden].detach().float(), b1[hidden:].detach().float()
+    w1p, b1p = pack_gated(a_w, a_b, g_w, g_b, half)
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), w1=w1p, b1=b1p, w2=_bf16(w2), b2=_f32(b2))
+    s = _lib.FFWeights(t["g"].data_ptr(), t["b"].data_ptr(), t["w1"].data_ptr(), t["b1"].data_ptr(),
+                       t["w2"].data_ptr(), t["b2"].data_ptr(), 2 * half)
+    return Packed(s, t)
+
+
+def pack_attention(norm_w, norm_b, wq, wkv, wg, bg, wo, bo, w_edge, dim_head: int) -> Packed:
+    scale = dim_head ** -0.5                                  # alphafold2.py:112,138 folded into to_q
+    wqkv = torch.cat([wq.detach().float() * scale, wkv.detach().float()], dim=0)
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), wqkv=_bf16(wqkv), wg=_bf16(wg), bg=_f32(bg), wo=_bf16(wo), bo=_f32(bo))
+    if w_edge is not None:
+        t["we"] = _f32(w_edge)
+    s = _lib.AttnWeights(t["g"].data_ptr(), t["b"].data_ptr(), t["wqkv"].data_ptr(), t["wg"].data_ptr(),
+                         t["bg"].data_ptr(), t["wo"].data_ptr(), t["bo"].data_ptr(),
+                         t["we"].data_ptr() if w_edge is not None else None)
+    return Packed(s, t)
+
+
+def pack_triangle_multiply(norm_w, norm_b, wl, bl, wr, br, wlg, blg, wrg, brg, wog, bog, onw, onb, wo, bo) -> Packed:
+    d = wl.shape[0]
+    half = gated_half(d)
+    f = lambda x: x.detach().float()  # noqa: E731
+    wlp, blp = pack_gated(f(wl), f(bl), f(wlg), f(blg), half)
+    wrp, brp = pack_gated(f(wr), f(br), f(wrg), f(brg), half)
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), wl=wlp, bl=blp, wr=wrp, br=brp, wog=_bf16(wog), bog=_f32(bog),
+             ong=_f32(onw), onb=_f32(onb), wo=_bf16(wo), bo=_f32(bo))
+    s = _lib.TriMulWeights(t["g"].data_ptr(), t["b"].data_ptr(), t["wl"].data_ptr(), t["bl"].data_ptr(),
+                           t["wr"].data_ptr(), t["br"].data_ptr(), t["wog"].data_ptr(), t["bog"].data_ptr(),
+                           t["ong"].data_ptr(), t["onb"].data_ptr(), t["wo"].data_ptr(), t["bo"].data_ptr(), 2 * half)
+    return Packed(s, t)
+
+
+def pack_outer_mean(norm_w, norm_b, wl, bl, wr, br, wo, bo) -> Packed:
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), wlr=_bf16(torch.cat([wl.detach(), wr.detach()], 0)),
+             blr=_f32(torch.cat([bl.detach(), br.detach()], 0)), wo=_bf16(wo), bo=_f32(bo))
+    s = _lib.OuterWeights(t["g"].data_ptr(), t["b"].data_ptr(), t["wlr"].data_ptr(), t["blr"].data_ptr(),
+                          t["wo"].data_ptr(), t["bo"].data_ptr())
+    return Packed(s, t)
+
+
+# --------------------------------------------------------------------------------------------------
+# ops (all in place on the fp32 residual stream)
+# --------------------------------------------------------------------------------------------------
+def feed_forward_(pk: Packed, x: torch.Tensor) -> torch.Tensor:
+    """x [..., d] fp32  <-  x + FeedForward(x)   (alphafold2.py:74-94, 439, 444)."""
+    _require(x, torch.float32, "x")
+    lib = _lib.load()
+    d = x.shape[-1]
+    tokens = x.numel() // d
+    hidden = pk.tensors["w2"].shape[1]
+    nbytes = lib.af2_feed_forward_workspace(tokens, d, hidden)
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.af2_feed_forward(C.byref(pk.struct), x.data_ptr(), tokens, d, hidden, ws.data_ptr(), ws.numel(),
+                                    _stream_ptr()))
+    return x
+
+
+def axial_attention_(pk: Packed, x: torch.Tensor, heads: int, dim_head: int, row_attn: bool,
+                     edges: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [b, h, w, d] fp32  <-  x + AxialAttention(x, edges, mask)   (alphafold2.py:192-255, 98-190)."""
+    _require(x, torch.float32, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be [b, h, w, d]")
+    B, h, w, d = x.shape
+    n = w if row_attn else h
+    if edges is not None:
+        _require(edges, torch.float32, "edges")
+        if tuple(edges.shape) != (B, n, n, d):
+            raise ValueError(f"edges must be [{B}, {n}, {n}, {d}], got {tuple(edges.shape)}")
+        if "we" not in pk.tensors:
+            edges = None                      # module built without accept_edges: the reference ignores edges
+    mask = _mask_u8(mask, (B, h, w), "mask")
+    lib = _lib.load()
+    nbytes = lib.af2_axial_attention_workspace(B, h, w, d, heads, dim_head, int(row_attn))
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.af2_axial_attention(C.byref(pk.struct), x.data_ptr(), _ptr(edges), _ptr(mask), B, h, w, d, heads,
+                                       dim_head, int(row_attn), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return x
+
+
+def triangle_multiply_(pk: Packed, x: torch.Tensor, ingoing: bool, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [b, N, N, d] fp32  <-  x + TriangleMultiplicativeModule(x, mask)   (alphafold2.py:257-317)."""
+    _require(x, torch.float32, "x")
+    assert x.dim() == 4 and x.shape[1] == x.shape[2], "feature map must be symmetrical"   # alphafold2.py:293
+    B, N, _, d = x.shape
+    mask = _mask_u8(mask, (B, N, N), "mask")
+    lib = _lib.load()
+    nbytes = lib.af2_triangle_multiply_workspace(B, N, d)
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.af2_triangle_multiply(C.byref(pk.struct), x.data_ptr(), _ptr(mask), B, N, d, int(ingoing),
+                                         ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return x
+
+
+def outer_mean_(pk: Packed, x: torch.Tensor, m: torch.Tensor, msa_mask: Optional[torch.Tensor] = None,
+                eps: float = 1e-5) -> torch.Tensor:
+    """x [b, N, N, d] fp32  <-  x + OuterMean(m, msa_mask)   (alphafold2.py:321-351, 379)."""
+    _require(x, torch.float32, "x")
+    _require(m, torch.float32, "m")
+    B, S, N, d = m.shape
+    if tuple(x.shape) != (B, N, N, d):
+        raise ValueError(f"x must be [{B}, {N}, {N}, {d}], got {tuple(x.shape)}")
+    msa_mask = _mask_u8(msa_mask, (B, S, N), "msa_mask")
+    lib = _lib.load()
+    nbytes = lib.af2_outer_mean_workspace(B, S, N, d)
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.af2_outer_mean(C.byref(pk.struct), x.data_ptr(), m.data_ptr(), _ptr(msa_mask), B, S, N, d,
+                                  float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return x
+
+
+def apply_rotary_pos_emb(x: torch.Tensor, sinu_pos) -> torch.Tensor:
+    """rotary.py:15-20.  x [b, h, n, dh] fp32, sinu_pos = (sin, cos) each [1 or b, n, rot]."""
+    sin, cos = sinu_pos
+    _require(x, torch.float32, "x")
+    sin, cos = sin.contiguous().float(), cos.contiguous().float()
+    b, h, n, dh = x.shape
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().af2_rotary(x.data_ptr(), sin.data_ptr(), cos.data_ptr(), y.data_ptr(), b, h, n, dh,
+                                      sin.shape[-1], sin.shape[0], _stream_ptr()))
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# building blocks exported for the parity tests
+# --------------------------------------------------------------------------------------------------
+def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _require(x, torch.float32, "x")
+    d = x.shape[-1]
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().af2_layernorm_bf16(x.data_ptr(), _f32(gamma).data_ptr(), _f32(beta).data_ptr(), y.data_ptr(),
+                                              x.numel() // d, d, float(eps), _stream_ptr()))
+    return y
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, mn_major: bool = False) -> torch.Tensor:
+    """a [batch, M, K] x b [batch, N, K] -> [batch, M, N]  (mn_major: a [batch, K, M], b [batch, K, N])."""
+    _require(a, torch.bfloat16, "a")
+    _require(b, torch.bfloat16, "b")
+    if mn_major:
+        batch, K, M = a.shape
+        N = b.shape[2]
+        lda, ldb = M, N
+    else:
+        batch, M, K = a.shape
+        N = b.shape[1]
+        lda, ldb = K, K
+    ldc = (N + 3) // 4 * 4
+    c = torch.empty(batch, M, ldc, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().af2_gemm_bf16_f32(a.data_ptr(), lda, a.shape[1] * a.shape[2], b.data_ptr(), ldb,
+                                             b.shape[1] * b.shape[2], c.data_ptr(), ldc, M * ldc, M, N, K, batch,
+                                             int(mn_major), _stream_ptr()))
+    return c[:, :, :N]

@@ -1,0 +1,115 @@
+/* libaf2b200.so — C ABI of the B200-native Evoformer trunk hot path.
+ *
+ * The reference (lucidrains/alphafold2 @ 931466e) is 100 % Python and has no FFI: its boundary for this
+ * path is the nn.Module API (alphafold2_pytorch/alphafold2.py).  Each entry point below therefore replaces
+ * the forward() of one reference module and is bound from Python with ctypes (alphafold2_b200/_lib.py);
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device (sm_100a only); nothing is allocated
+ *     or retained by the library: outputs and workspace are caller-owned;
+ *   - activations x / m are fp32, channel-last, contiguous; weights are packed bf16 (see packing.py) with
+ *     fp32 biases / LayerNorm affine parameters; masks are 1-byte bools (torch.bool);
+ *   - residual adds are performed in place on the fp32 stream (x <- x + f(x));
+ *   - launches are asynchronous on `stream` (a cudaStream_t); CUDA-graph capturable (no sync, no malloc);
+ *   - return 0 on success, negative on error (af2_last_error() holds the message). There is NO CPU fallback.
+ */
+#ifndef AF2B200_H
+#define AF2B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* af2_stream_t; /* cudaStream_t */
+
+#define AF2_OK 0
+#define AF2_ERR_BAD_ARG (-1)
+#define AF2_ERR_CUDA (-2)
+#define AF2_ERR_UNSUPPORTED_DEVICE (-3)
+#define AF2_ERR_WORKSPACE (-4)
+
+const char* af2_last_error(void);
+int af2_abi_version(void);
+/* 0 if the current device is compute capability 10.x, AF2_ERR_UNSUPPORTED_DEVICE otherwise */
+int af2_check_device(void);
+
+/* ---------------- FeedForward: alphafold2.py:74-94 (+ residual of :439 / :444) -----------------------
+ * x <- x + W2 (a * gelu_erf(g)) + b2,  [a|g] = W1 LN(x) + b1.
+ * w1 is packed per column tile of `bn` accumulator columns as [bn/2 value rows | bn/2 gate rows]
+ * (zero rows pad the last tile); b1 is permuted the same way. */
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* FeedForward.norm          [d]            */
+  const void* w1; const float* b1;                    /* FeedForward.net.0         packed [n1p, d]  */
+  const void* w2; const float* b2;                    /* FeedForward.net.3         [d, hid] , [d]   */
+  int bn;                                             /* column tile used for the w1 packing        */
+} af2_ff_weights;
+int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d, int hidden,
+                     void* workspace, long long workspace_bytes, af2_stream_t stream);
+long long af2_feed_forward_workspace(long long tokens, int d, int hidden);
+
+/* ---------------- AxialAttention: alphafold2.py:192-255 driving Attention :98-190 (+ residual) --------
+ * x [B, h, w, d] <- x + to_out( softmax(q k^T + bias, mask) v * sigmoid(gating) ).
+ * row_attn = 1: attend along w for every (b, h) row; 0: along h for every (b, w) column.
+ * edges: RAW fp32 pair tensor [B, n, n, d] (n = attended length) or NULL; bias = edges . w_edge^T,
+ * identical for every folded row/column, orientation [head, query, key] (quirks Q4/Q5). */
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* AxialAttention.norm                        */
+  const void* w_qkv;                                  /* [3I, d]: to_q * dim_head^-0.5 | to_kv      */
+  const void* w_gate; const float* b_gate;            /* Attention.gating          [I, d], [I]      */
+  const void* w_out; const float* b_out;              /* Attention.to_out          [d, I], [d]      */
+  const float* w_edge;                                /* edges_to_attn_bias.0      [H, d] fp32/NULL */
+} af2_attn_weights;
+int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask,
+                        int B, int h, int wdim, int d, int heads, int dim_head, int row_attn,
+                        void* workspace, long long workspace_bytes, af2_stream_t stream);
+long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads, int dim_head, int row_attn);
+
+/* ---------------- TriangleMultiplicativeModule: alphafold2.py:257-317 (+ residual :381-382) ----------
+ * x [B, N, N, d] <- x + to_out( LN_c( mix(L, R) ) * sigmoid(out_gate) ),  hidden_dim == d.
+ * outgoing (mix=0): O[i,j,c] = sum_k L[i,k,c] R[j,k,c];  ingoing (mix=1): O[i,j,c] = sum_k L[k,j,c] R[k,i,c].
+ * w_left / w_right are packed per tile as [value rows | gate rows] like w1 above. */
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* .norm                                      */
+  const void* w_left; const float* b_left;            /* left_proj + left_gate, packed              */
+  const void* w_right; const float* b_right;          /* right_proj + right_gate, packed            */
+  const void* w_ogate; const float* b_ogate;          /* out_gate                  [d, d], [d]      */
+  const float* on_gamma; const float* on_beta;        /* to_out_norm                                */
+  const void* w_out; const float* b_out;              /* to_out                    [d, d], [d]      */
+  int bn;
+} af2_trimul_weights;
+int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned char* mask, int B, int N, int d,
+                          int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream);
+long long af2_triangle_multiply_workspace(int B, int N, int d);
+
+/* ---------------- OuterMean: alphafold2.py:321-351 (+ residual :379) ---------------------------------
+ * x [B, N, N, d] <- x + proj_out( sum_s L[s,i,:] * R[s,j,:] / S  [/ (count_ij + eps) when masked] ).
+ * Never materialises the (S, N, N, d) tensor of alphafold2.py:341. */
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* .norm                                      */
+  const void* w_lr; const float* b_lr;                /* [2d, d]: left_proj | right_proj, [2d]      */
+  const void* w_out; const float* b_out;              /* proj_out                  [d, d], [d]      */
+} af2_outer_weights;
+int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask,
+                   int B, int S, int N, int d, float eps, void* workspace, long long workspace_bytes,
+                   af2_stream_t stream);
+long long af2_outer_mean_workspace(int B, int S, int N, int d);
+
+/* ---------------- rotary.py:9-20 apply_rotary_pos_emb (dead code at HEAD; standalone op) -------------
+ * x, y [b, h, n, dh] fp32; sin, cos [sincos_batch, n, rot] with sincos_batch in {1, b}. */
+int af2_rotary(const float* x, const float* sin_, const float* cos_, float* y, int b, int h, int n, int dh,
+               int rot, int sincos_batch, af2_stream_t stream);
+
+/* ---------------- building blocks, exported for the parity tests -------------------------------------- */
+/* y_bf16[T, d] = LayerNorm(x) (nn.LayerNorm semantics) */
+int af2_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* y_bf16, long long T, int d,
+                       float eps, af2_stream_t stream);
+/* C[b] = A[b] B[b]^T (mn_major = 0: A [M,K], B [N,K]) or A[b]^T B[b] (mn_major = 1: A [K,M], B [K,N]);
+ * bf16 operands, fp32 accumulation, fp32 output C [batch, M, ldc]. */
+int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const void* Bm, long long ldb,
+                      long long b_batch, float* C, long long ldc, long long c_batch, int M, int N, int K,
+                      int batch, int mn_major, af2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AF2B200_H */
