@@ -35,6 +35,9 @@ _SIGNATURES = {
     "af2_last_error": (C.c_char_p, []),
     "af2_abi_version": (ci, []),
     "af2_check_device": (ci, []),
+    "af2_launch_count": (C.c_ulonglong, []),
+    "af2_profile_enable": (None, [ci]),
+    "af2_profile_read": (ll, [ci, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "af2_feed_forward": (ci, [C.POINTER(FFWeights), vp, ll, ci, ci, vp, ll, vp]),
     "af2_feed_forward_workspace": (ll, [ll, ci, ci]),
     "af2_axial_attention": (ci, [C.POINTER(AttnWeights), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/af2b200.h"
 #include "attention_tc.cuh"
@@ -49,6 +50,29 @@ int sm_count() {
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch accounting + optional per-kernel-class CUDA-event profiling (bench.py roofline numbers)
+// ---------------------------------------------------------------------------------------------
+enum KClass { KC_GEMM_LINEAR = 0, KC_GEMM_CHANNEL = 1, KC_ATTENTION = 2, KC_LAYERNORM = 3, KC_CHAN2TOK = 4, KC_MISC = 5, KC_COUNT = 6 };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+unsigned long long g_launches = 0;
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+
+cudaEvent_t prof_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  cudaStream_t s; bool on; ProfRec r;
+  ProfScope(cudaStream_t st, int cls, double flops, double bytes) : s(st), on(g_prof) {
+    ++g_launches;
+    if (on) { r.a = prof_event(); r.b = prof_event(); r.cls = cls; r.flops = flops; r.bytes = bytes; cudaEventRecord(r.a, s); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, s); g_recs.push_back(r); } }
+};
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -63,7 +87,8 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // bf16 tensor map. dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
 int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
-              const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
+              const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz,
+              CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   auto fn = encode_fn();
   if (!fn) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -78,7 +103,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail(AF2_ERR_BAD_ARG, "TMA base pointer not 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i)
     if (gstr[i] & 15) return fail(AF2_ERR_BAD_ARG, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gstr[i]);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -123,11 +148,12 @@ struct GemmCall {
   int out_cols;           // 0: N (N/2 for GATED); else explicit number of valid output columns
 };
 
-template <int BN, int STAGES, bool MN>
-int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+template <int BN, int STAGES, bool MN, int EK>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                     const GemmParams& p, cudaStream_t s) {
   using L = GemmSmem<BN, STAGES>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, MN>;
+  auto kern = gemm_tc_kernel<BN, STAGES, MN, EK>;
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
@@ -136,7 +162,12 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   const long long total = (long long)p.batch * m_tiles * p.num_ntiles;
   if (total <= 0) return AF2_OK;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, 256, L::TOTAL, s>>>(ta, tb, p);
+  const double flops = 2.0 * p.batch * (double)p.M * p.N * p.K;
+  const double obytes = (p.tile.mode == EPI_STORE_BF16 ? 2.0 : (p.tile.mode == EPI_GATED_BF16 ? 1.0 : (p.tile.mode == EPI_RESID_F32 ? 8.0 : 4.0)));
+  const double bytes = p.batch * ((double)p.M * p.K * 2 + (p.batch > 1 ? (double)p.N * p.K * 2 : 0) + (double)p.M * p.N * obytes) +
+                       (p.batch > 1 ? 0 : (double)p.N * p.K * 2);
+  ProfScope ps(s, p.batch > 1 ? KC_GEMM_CHANNEL : KC_GEMM_LINEAR, flops, bytes);
+  kern<<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, tc, tr, p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }
@@ -173,14 +204,73 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
   p.cm_inner = c.cm_inner > 0 ? c.cm_inner : 1; p.cm_pitch = c.cm_pitch > 0 ? c.cm_pitch : 1;
   p.tile.mode = c.mode; p.tile.act = c.act; p.tile.layout = c.layout; p.tile.use_rowscale = c.use_rowscale;
   p.tile.out = c.out; p.tile.bias = c.bias; p.tile.ld = c.ld_out;
-  if (c.mn_major) {
-    if (BN == 256) return launch_gemm_inst<256, 4, true>(ta, tb, p, s);
-    if (BN == 128) return launch_gemm_inst<128, 6, true>(ta, tb, p, s);
-    return launch_gemm_inst<64, 8, true>(ta, tb, p, s);
+  // ---- output path: TMA store through swizzled smem staging whenever the output is a legal TMA tensor ----
+  const bool out_f32 = (c.mode == EPI_RESID_F32 || c.mode == EPI_STORE_F32);
+  const int es = out_f32 ? 4 : 2;
+  const int W = (c.mode == EPI_GATED_BF16) ? BN / 2 : BN;
+  bool direct = false;
+  if (!out_f32 && (W % 64) != 0) direct = true;
+  if ((reinterpret_cast<uintptr_t>(c.out) & 15) != 0) direct = true;
+  if (c.layout == LAYOUT_TOKEN) {
+    if ((c.ld_out * es) % 16 != 0) direct = true;
+    if (c.batch > 1 && (c.out_batch * es) % 16 != 0) direct = true;
+  } else {
+    if (c.cm_pitch != c.cm_inner || (c.ld_out * 2) % 16 != 0 || c.batch != 1 || out_f32) direct = true;
   }
-  if (BN == 256) return launch_gemm_inst<256, 4, false>(ta, tb, p, s);
-  if (BN == 128) return launch_gemm_inst<128, 6, false>(ta, tb, p, s);
-  return launch_gemm_inst<64, 8, false>(ta, tb, p, s);
+  if (c.mode == EPI_RESID_F32 && ((c.ld_resid * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(c.resid) & 15) != 0)) direct = true;
+  CUtensorMap tc = ta, tr = ta;
+  if (!direct) {
+    const CUtensorMapDataType dt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (c.layout == LAYOUT_TOKEN) {
+      unsigned long long dc[3] = {(unsigned long long)p.out_cols, (unsigned long long)c.M, (unsigned long long)c.batch};
+      unsigned long long sc[2] = {(unsigned long long)c.ld_out * es, (unsigned long long)(c.batch > 1 ? c.out_batch : c.ld_out * c.M) * es};
+      unsigned bc[3] = {(unsigned)(out_f32 ? 32 : 64), 128, 1};
+      AF2_TRY(make_tmap(&tc, c.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
+      if (c.mode == EPI_RESID_F32) {
+        unsigned long long sr[2] = {(unsigned long long)c.ld_resid * 4, (unsigned long long)c.ld_resid * c.M * 4};
+        AF2_TRY(make_tmap(&tr, c.resid, 3, dc, sr, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
+      }
+    } else {
+      unsigned long long dc[3] = {(unsigned long long)c.M, (unsigned long long)p.out_cols, 1ull};
+      unsigned long long sc[2] = {(unsigned long long)c.ld_out * 2, (unsigned long long)c.ld_out * p.out_cols * 2};
+      unsigned bc[3] = {64, 64, 1};
+      AF2_TRY(make_tmap(&tc, c.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
+    }
+  }
+  p.direct = direct ? 1 : 0;
+  // compile-time epilogue specialisation for the big-tile instantiation
+  int ek = EK_GENERIC;
+  if (!direct && BN == 256) {
+    if (c.mode == EPI_STORE_BF16 && c.layout == LAYOUT_TOKEN && c.act == ACT_NONE && !c.use_rowscale) ek = EK_STORE_TOK;
+    else if (c.mode == EPI_STORE_BF16 && c.layout == LAYOUT_TOKEN && c.act == ACT_SIGMOID && !c.use_rowscale) ek = EK_STORE_TOK_SIG;
+    else if (c.mode == EPI_STORE_BF16 && c.layout == LAYOUT_CHANNEL && c.act == ACT_NONE) ek = EK_STORE_CH;
+    else if (c.mode == EPI_GATED_BF16 && c.layout == LAYOUT_TOKEN && c.act == ACT_GELU && !c.use_rowscale) ek = EK_GATED_TOK_GELU;
+    else if (c.mode == EPI_GATED_BF16 && c.layout == LAYOUT_CHANNEL && c.act == ACT_SIGMOID) ek = EK_GATED_CH_SIG;
+    else if (c.mode == EPI_RESID_F32) ek = EK_RESID_F32;
+    else if (c.mode == EPI_STORE_F32) ek = EK_STORE_F32;
+  }
+  if (c.mn_major) {
+    if (BN == 256) {
+      if (ek == EK_STORE_F32) return launch_gemm_inst<256, 3, true, EK_STORE_F32>(ta, tb, tc, tr, p, s);
+      return launch_gemm_inst<256, 3, true, EK_GENERIC>(ta, tb, tc, tr, p, s);
+    }
+    if (BN == 128) return launch_gemm_inst<128, 4, true, EK_GENERIC>(ta, tb, tc, tr, p, s);
+    return launch_gemm_inst<64, 6, true, EK_GENERIC>(ta, tb, tc, tr, p, s);
+  }
+  if (BN == 256) {
+    switch (ek) {
+      case EK_STORE_TOK: return launch_gemm_inst<256, 3, false, EK_STORE_TOK>(ta, tb, tc, tr, p, s);
+      case EK_STORE_TOK_SIG: return launch_gemm_inst<256, 3, false, EK_STORE_TOK_SIG>(ta, tb, tc, tr, p, s);
+      case EK_STORE_CH: return launch_gemm_inst<256, 3, false, EK_STORE_CH>(ta, tb, tc, tr, p, s);
+      case EK_GATED_TOK_GELU: return launch_gemm_inst<256, 3, false, EK_GATED_TOK_GELU>(ta, tb, tc, tr, p, s);
+      case EK_GATED_CH_SIG: return launch_gemm_inst<256, 3, false, EK_GATED_CH_SIG>(ta, tb, tc, tr, p, s);
+      case EK_RESID_F32: return launch_gemm_inst<256, 3, false, EK_RESID_F32>(ta, tb, tc, tr, p, s);
+      case EK_STORE_F32: return launch_gemm_inst<256, 3, false, EK_STORE_F32>(ta, tb, tc, tr, p, s);
+      default: return launch_gemm_inst<256, 3, false, EK_GENERIC>(ta, tb, tc, tr, p, s);
+    }
+  }
+  if (BN == 128) return launch_gemm_inst<128, 4, false, EK_GENERIC>(ta, tb, tc, tr, p, s);
+  return launch_gemm_inst<64, 6, false, EK_GENERIC>(ta, tb, tc, tr, p, s);
 }
 
 int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
@@ -202,6 +292,7 @@ int launch_layernorm(const LnParams& p, cudaStream_t s) {
   const long long blocks_needed = (p.T + 7) / 8;
   const long long cap = (long long)sm_count() * 16;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  ProfScope ps(s, KC_LAYERNORM, 0.0, (double)p.T * p.d * (p.y ? 6.0 : 4.0) + (p.wb ? (double)p.T * p.heads * 2 : 0));
   if (p.d <= 128) layernorm_rows_kernel<1><<<grid, 256, 0, s>>>(p);
   else if (p.d <= 256) layernorm_rows_kernel<2><<<grid, 256, 0, s>>>(p);
   else if (p.d <= 512) layernorm_rows_kernel<4><<<grid, 256, 0, s>>>(p);
@@ -218,6 +309,7 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
     configured = smem;
   }
   dim3 grid((p.n + 31) / 32, p.rows);
+  ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)p.rows * p.n * p.d * (p.mode == 0 ? 8.0 : 6.0));
   chan_to_token_kernel<<<grid, 256, smem, s>>>(p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
@@ -237,6 +329,9 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     configured = true;
   }
   dim3 grid((p.n + 127) / 128, p.heads, p.nbatch);
+  const double tokens = (double)p.n * p.nbatch;
+  ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
+               tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
   kern<<<grid, 192, L::TOTAL, s>>>(tq, tk, tv, tbias, p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
@@ -289,6 +384,33 @@ extern "C" {
 
 const char* af2_last_error(void) { return g_err; }
 int af2_abi_version(void) { return 1; }
+
+unsigned long long af2_launch_count(void) { return g_launches; }
+
+void af2_profile_enable(int on) {
+  g_prof = on != 0;
+  if (g_prof) {
+    for (auto& r : g_recs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+    g_recs.clear();
+  }
+}
+
+// Sums the recorded launches of kernel class `cls` (synchronises the device). Returns the launch count.
+long long af2_profile_read(int cls, double* ms, double* flops, double* bytes) {
+  cudaDeviceSynchronize();
+  double t = 0, f = 0, b = 0;
+  long long n = 0;
+  for (auto& r : g_recs) {
+    if (r.cls != cls) continue;
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) t += e;
+    f += r.flops; b += r.bytes; ++n;
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (bytes) *bytes = b;
+  return n;
+}
 
 int af2_check_device(void) {
   int dev = 0;
@@ -439,7 +561,7 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
   AF2_TRY(launch_layernorm(lp, s));
   if (mask) {
-    mask_to_float_kernel<<<ew_grid(T), 256, 0, s>>>(mask, maskf, T);
+    { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(T), 256, 0, s>>>(mask, maskf, T); }
     CUDA_OK(cudaGetLastError());
   }
   if (np8 != N) {   // pad columns of the channel-major operands are read by TMA as K / MN padding: keep them zero
@@ -518,9 +640,9 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   lp.x = m; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = mn; lp.T = Tm; lp.d = d; lp.eps = 1e-5f;
   AF2_TRY(launch_layernorm(lp, s));
   if (msa_mask) {
-    mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm);
+    { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm); }
     CUDA_OK(cudaGetLastError());
-    outer_scale_kernel<<<ew_grid(Tx), 256, 0, s>>>(msa_mask, scale, B, S, N, eps);
+    { ProfScope ps(s, KC_MISC, 0.0, 0.0); outer_scale_kernel<<<ew_grid(Tx), 256, 0, s>>>(msa_mask, scale, B, S, N, eps); }
     CUDA_OK(cudaGetLastError());
   }
   if (np8 != N) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * cs_lr * 2, s));
@@ -557,7 +679,7 @@ int af2_rotary(const float* x, const float* sin_, const float* cos_, float* y, i
   if (dh % 2 || rot % 2 || rot > dh) return fail(AF2_ERR_BAD_ARG, "rotary: dh=%d rot=%d must be even, rot <= dh", dh, rot);
   const long long pairs = (long long)b * h * n * (dh / 2);
   if (pairs == 0) return AF2_OK;
-  rotary_kernel<<<ew_grid(pairs), 256, 0, s>>>(x, sin_, cos_, y, b, h, n, dh, rot, sincos_batch);
+  { ProfScope ps(s, KC_MISC, 0.0, 0.0); rotary_kernel<<<ew_grid(pairs), 256, 0, s>>>(x, sin_, cos_, y, b, h, n, dh, rot, sincos_batch); }
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }

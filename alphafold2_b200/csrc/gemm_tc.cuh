@@ -1,5 +1,6 @@
-// Generic batched bf16 GEMM on tcgen05 tensor cores with TMA-staged operands and a programmable
-// per-column-tile epilogue.  One kernel serves every dense contraction of the Evoformer block:
+// Generic batched bf16 GEMM on tcgen05 tensor cores with TMA-staged operands and a programmable epilogue
+// whose results leave the SM through shared memory + TMA stores (coalesced, OOB-clipped by hardware).
+// One kernel serves every dense contraction of the Evoformer block:
 //
 //   K-major mode  : C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]      (Linear layers: B = weight [out,in];
 //                                                                    triangle "outgoing" per channel)
@@ -7,10 +8,15 @@
 //                                                                    channel-major operands, k = row axis)
 //
 // Tiling: BM = 128 rows (one TMEM lane per row), BN in {64,128,256} accumulator columns, BK = 64.
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).  Persistent over
-// tiles; the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
-// tile i+1.  Operands use the 128B swizzle written by TMA and read back by the UMMA descriptors.
+// Warp roles (384 threads):
+//   warp 0  TMA producer of A/B stages          warp 1  MMA issuer (one elected lane)
+//   warp 2  TMEM allocator                      warp 3  epilogue staging-buffer producer (residual TMA loads)
+//   warps 4..11  epilogue, two groups of four: TMEM -> registers -> (bias, activation, gate, mask, residual) ->
+//               swizzled smem staging buffer -> TMA store (one leader thread per group issues)
+// Persistent over tiles; the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
+// MMAs of tile i+1; four 16 KB staging buffers pipeline the stores.  When the output cannot be described by a
+// TMA tensor (ragged channel-major pitch, unaligned leading dimension, tiny BN) the epilogue falls back to
+// direct (slow, still correct) global stores.
 #pragma once
 #include "common.cuh"
 
@@ -18,31 +24,31 @@ namespace af2 {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
+constexpr int EPI_BUFS = 4;
+constexpr int EPI_BUF_BYTES = 16384;
 
 enum EpiMode : int { EPI_STORE_BF16 = 0, EPI_GATED_BF16 = 1, EPI_RESID_F32 = 2, EPI_STORE_F32 = 3 };
 enum EpiAct : int { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_GELU = 2 };
 enum EpiLayout : int { LAYOUT_TOKEN = 0, LAYOUT_CHANNEL = 1 };
 
-// Epilogue program of one BN-wide accumulator column tile.
+// Epilogue program (identical for every column tile).
 struct NTile {
   int mode;        // EpiMode
   int act;         // EpiAct (applied to the value for STORE, to the gate half for GATED)
   int layout;      // EpiLayout
-  int col0;        // first output column (token-major) / first output channel (channel-major)
-  int ncols;       // number of valid OUTPUT columns of this tile
   int use_rowscale;
   void* out;
-  const float* bias;   // [BN] accumulator-column bias of this tile, or nullptr
+  const float* bias;   // [N] accumulator-column bias, or nullptr
   long long ld;        // token-major: row stride (elements); channel-major: channel stride (elements)
 };
 
-// Every column tile runs the same epilogue program `tile`; tile nt produces output columns
-// [nt*W, nt*W + W) with W = BN (BN/2 for EPI_GATED, whose weight rows are packed per tile as
-// [value rows of the tile | gate rows of the tile]), clipped to out_cols.
+// Tile nt produces output columns [nt*W, nt*W + W) with W = BN (BN/2 for EPI_GATED, whose weight rows are
+// packed per tile as [value rows of the tile | gate rows of the tile]), clipped to out_cols.
 struct GemmParams {
   int M, N, K, batch;          // N = accumulator columns = rows of the B operand
   int num_ntiles;
   int out_cols;                // valid output columns (N, or N/2 for EPI_GATED)
+  int direct;                  // 1: direct global stores (no TMA store)
   const float* rowscale;       // [batch*M] multiplier per row (mask), or nullptr
   const float* resid;          // EPI_RESID_F32: fp32 [M, ld_resid]
   long long ld_resid;
@@ -56,13 +62,99 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;       // barriers + 1 KB alignment slack
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;       // barriers + 1 KB alignment slack
 };
 
-template <int BN, int STAGES, bool MN_MAJOR>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_SIGMOID) return sigmoidf_fast(x);
+  if (act == ACT_GELU) return gelu_erf(x);
+  return x;
+}
+
+// Compile-time epilogue specialisations (EK_GENERIC reads mode / act / layout from the params at run time; it is
+// used for the small-tile instantiations where speed does not matter).
+enum EpiKind : int {
+  EK_GENERIC = 0,
+  EK_STORE_TOK = 1,       // bf16 token-major, optional bias                       (q|k|v projection)
+  EK_STORE_TOK_SIG = 2,   // bf16 token-major, sigmoid(acc + bias)                  (attention gate, out_gate)
+  EK_STORE_CH = 3,        // bf16 channel-major, (acc + bias) * rowscale            (outer-mean left|right)
+  EK_GATED_TOK_GELU = 4,  // bf16 token-major, (u + b) * gelu(g + b)                (FeedForward first Linear)
+  EK_GATED_CH_SIG = 5,    // bf16 channel-major, (u + b) * sigmoid(g + b) * rowscale (triangle left / right)
+  EK_RESID_F32 = 6,       // fp32 token-major, acc + bias + residual                (every output projection)
+  EK_STORE_F32 = 7        // fp32 token-major                                       (per-channel contractions)
+};
+template <int EK> struct EpiTraits { static constexpr int mode = -1, act = -1, layout = -1; static constexpr bool rowscale = true; };
+template <> struct EpiTraits<EK_STORE_TOK> { static constexpr int mode = EPI_STORE_BF16, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+template <> struct EpiTraits<EK_STORE_TOK_SIG> { static constexpr int mode = EPI_STORE_BF16, act = ACT_SIGMOID, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+template <> struct EpiTraits<EK_STORE_CH> { static constexpr int mode = EPI_STORE_BF16, act = ACT_NONE, layout = LAYOUT_CHANNEL; static constexpr bool rowscale = true; };
+template <> struct EpiTraits<EK_GATED_TOK_GELU> { static constexpr int mode = EPI_GATED_BF16, act = ACT_GELU, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+template <> struct EpiTraits<EK_GATED_CH_SIG> { static constexpr int mode = EPI_GATED_BF16, act = ACT_SIGMOID, layout = LAYOUT_CHANNEL; static constexpr bool rowscale = true; };
+template <> struct EpiTraits<EK_RESID_F32> { static constexpr int mode = EPI_RESID_F32, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+template <> struct EpiTraits<EK_STORE_F32> { static constexpr int mode = EPI_STORE_F32, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+
+__device__ __forceinline__ void load_bias32(const float* b, float (&bv)[32]) {
+  if (b) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(b) + j);
+      bv[4 * j] = t4.x; bv[4 * j + 1] = t4.y; bv[4 * j + 2] = t4.z; bv[4 * j + 3] = t4.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+  }
+}
+
+// 32 accumulator columns starting at tile-local column c -> finished values (bias, activation / gate, row scale)
+template <int BN, int EK>
+__device__ __forceinline__ void epi_values(uint32_t t_acc, int c, int mode, int act, const float* bias_tile, float rs,
+                                           float (&v)[32]) {
+  uint32_t u[32];
+  tmem_ld32(t_acc + c, u);
+  if (mode == EPI_GATED_BF16) {
+    uint32_t g[32];
+    tmem_ld32(t_acc + BN / 2 + c, g);
+    float bu[32], bg[32];
+    load_bias32(bias_tile ? bias_tile + c : nullptr, bu);
+    load_bias32(bias_tile ? bias_tile + BN / 2 + c : nullptr, bg);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float uu = __uint_as_float(u[j]) + bu[j], gg = __uint_as_float(g[j]) + bg[j];
+      v[j] = uu * apply_act(gg, act);
+      if (EpiTraits<EK>::rowscale) v[j] *= rs;
+    }
+  } else {
+    float bu[32];
+    load_bias32(bias_tile ? bias_tile + c : nullptr, bu);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = apply_act(__uint_as_float(u[j]) + bu[j], act);
+      if (EpiTraits<EK>::rowscale) v[j] *= rs;
+    }
+  }
+}
+
+constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
+
+template <int BN, int STAGES, bool MN_MAJOR, int EK>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -71,7 +163,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* efull_bar = tempty_bar + 2;         // [EPI_BUFS] staging buffer free (+ residual landed)
+  uint64_t* eempty_bar = efull_bar + EPI_BUFS;  // [EPI_BUFS] staging buffer released by its TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty_bar + EPI_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (!p.direct) prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -88,7 +183,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);   // one arrive per epilogue warp
+    }
+    for (int s = 0; s < EPI_BUFS; ++s) {
+      mbar_init(&efull_bar[s], 1);
+      mbar_init(&eempty_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -102,6 +201,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = p.num_ntiles;
   const int total_tiles = p.batch * m_tiles * n_tiles;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  // epilogue geometry shared by the staging producer (warp 3) and the epilogue warps
+  const int e_mode = (EK == EK_GENERIC) ? p.tile.mode : EpiTraits<EK>::mode;
+  const int e_act = (EK == EK_GENERIC) ? p.tile.act : EpiTraits<EK>::act;
+  const int e_layout = (EK == EK_GENERIC) ? p.tile.layout : EpiTraits<EK>::layout;
+  const int W = (e_mode == EPI_GATED_BF16) ? BN / 2 : BN;                      // output columns per tile
+  const bool out_f32 = (e_mode == EPI_RESID_F32) || (e_mode == EPI_STORE_F32);
+  const int CW = out_f32 ? 32 : 64;                                            // output columns per staging chunk
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -172,149 +279,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== staging-buffer producer (residual prefetch) ==================
+    if (lane == 0 && !p.direct) {
+      uint32_t ec = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int mt = (tile / n_tiles) % m_tiles;
+        const int b = tile / (n_tiles * m_tiles);
+        const int ncols = min(W, p.out_cols - nt * W);
+        const int nchunks = (ncols + CW - 1) / CW;
+        for (int cc = 0; cc < nchunks; ++cc, ++ec) {
+          const int buf = ec % EPI_BUFS;
+          mbar_wait(&eempty_bar[buf], ((ec / EPI_BUFS) & 1) ^ 1);
+          if (e_mode == EPI_RESID_F32) {
+            mbar_arrive_expect_tx(&efull_bar[buf], EPI_BUF_BYTES);
+            tma_load_3d(smem + L::EPI_OFF + buf * EPI_BUF_BYTES, &tmR, &efull_bar[buf], nt * W + cc * CW,
+                        mt * GEMM_BM, b);
+          } else {
+            mbar_arrive(&efull_bar[buf]);
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
+    // Two groups of four warps (4..7 and 8..11); warp w may touch TMEM lanes 32*(w%4)..+31, so each group covers
+    // all 128 rows; the groups take alternating staging chunks (group g owns chunks with ec % 2 == g).
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;          // 0 / 1
     const int row_in_tile = q * 32 + lane;
+    const bool leader = (threadIdx.x == 128 + grp * 128);
+    const NTile t = p.tile;
     int it = 0;
+    uint32_t ec = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int b = tile / (n_tiles * m_tiles);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      NTile t = p.tile;
-      {
-        const int w = (t.mode == EPI_GATED_BF16) ? BN / 2 : BN;
-        t.col0 = nt * w;
-        t.ncols = min(w, p.out_cols - nt * w);
-        if (t.bias) t.bias += nt * BN;
-      }
+      const int col0 = nt * W;
+      const int ncols = min(W, p.out_cols - col0);
+      const float* bias_tile = t.bias ? t.bias + nt * BN : nullptr;
       const int row = mt * GEMM_BM + row_in_tile;
       const bool row_ok = row < p.M;
-      const long long grow = static_cast<long long>(b) * p.M + row;   // row index over the whole batch
       float rs = 1.0f;
-      if (t.use_rowscale && row_ok) rs = __ldg(p.rowscale + grow);
-      long long cm_off = 0;
-      if (t.layout == LAYOUT_CHANNEL) cm_off = static_cast<long long>(row / p.cm_inner) * p.cm_pitch + row % p.cm_inner;
+      if (t.use_rowscale && row_ok) rs = __ldg(p.rowscale + static_cast<long long>(b) * p.M + row);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-      if (t.mode == EPI_GATED_BF16) {
-        constexpr int HALF = BN / 2;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t.out) + b * p.out_batch_stride;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 32) {
-          uint32_t u[32], g[32];
-          tmem_ld32(t_acc + c0, u);
-          tmem_ld32(t_acc + HALF + c0, g);
-          tmem_ld_wait();
-          float v[32];
+      if (!p.direct) {
+        const int nchunks = (ncols + CW - 1) / CW;
+        for (int cc = 0; cc < nchunks; ++cc, ++ec) {
+          if ((ec & 1) != static_cast<uint32_t>(grp)) continue;
+          const int buf = ec % EPI_BUFS;
+          uint8_t* eb = smem + L::EPI_OFF + buf * EPI_BUF_BYTES;
+          mbar_wait(&efull_bar[buf], (ec / EPI_BUFS) & 1);
+          if (out_f32) {
+            float v[32];
+            epi_values<BN, EK>(t_acc, cc * 32, e_mode, e_act, bias_tile, rs, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float uu = __uint_as_float(u[j]), gg = __uint_as_float(g[j]);
-            if (t.bias) {
-              uu += __ldg(t.bias + c0 + j);
-              gg += __ldg(t.bias + HALF + c0 + j);
-            }
-            const float a = (t.act == ACT_GELU) ? gelu_erf(gg) : sigmoidf_fast(gg);
-            v[j] = uu * a * rs;
-          }
-          if (row_ok) {
-            if (t.layout == LAYOUT_TOKEN) {
-              __nv_bfloat16* dst = out + static_cast<long long>(row) * t.ld + t.col0 + c0;
-              if (c0 + 32 <= t.ncols) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                        pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-                  *reinterpret_cast<uint4*>(dst + j) = pk;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < t.ncols) dst[j] = __float2bfloat16(v[j]);
+            for (int j = 0; j < 8; ++j) {
+              float4* sp = reinterpret_cast<float4*>(eb + swz128_off(row_in_tile, j));
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (e_mode == EPI_RESID_F32) {
+                const float4 r4 = *sp;
+                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < t.ncols) out[static_cast<long long>(t.col0 + c0 + j) * t.ld + cm_off] = __float2bfloat16(v[j]);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (c0 >= t.ncols) break;           // warp-uniform
-          uint32_t u[32];
-          tmem_ld32(t_acc + c0, u);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(u[j]);
-            if (t.bias) x += __ldg(t.bias + c0 + j);
-            if (t.act == ACT_SIGMOID) x = sigmoidf_fast(x);
-            else if (t.act == ACT_GELU) x = gelu_erf(x);
-            v[j] = x * rs;
-          }
-          if (!row_ok) continue;
-          const bool full = (c0 + 32 <= t.ncols);
-          if (t.mode == EPI_STORE_BF16) {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t.out) + b * p.out_batch_stride;
-            if (t.layout == LAYOUT_TOKEN) {
-              __nv_bfloat16* dst = out + static_cast<long long>(row) * t.ld + t.col0 + c0;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                        pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-                  *reinterpret_cast<uint4*>(dst + j) = pk;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < t.ncols) dst[j] = __float2bfloat16(v[j]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < t.ncols) out[static_cast<long long>(t.col0 + c0 + j) * t.ld + cm_off] = __float2bfloat16(v[j]);
+              *sp = o;
             }
           } else {
-            float* out = reinterpret_cast<float*>(t.out) + b * p.out_batch_stride;
-            float* dst = out + static_cast<long long>(row) * t.ld + t.col0 + c0;
-            if (t.mode == EPI_RESID_F32) {
-              const float* rsd = p.resid + static_cast<long long>(row) * p.ld_resid + t.col0 + c0;
-              if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(rsd + j);
-                  *reinterpret_cast<float4*>(dst + j) =
-                      make_float4(v[j] + r4.x, v[j + 1] + r4.y, v[j + 2] + r4.z, v[j + 3] + r4.w);
+            for (int half = 0; half < 2; ++half) {
+              float v[32];
+              epi_values<BN, EK>(t_acc, cc * 64 + half * 32, e_mode, e_act, bias_tile, rs, v);
+              if (e_layout == LAYOUT_TOKEN) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                  *reinterpret_cast<uint4*>(eb + swz128_off(row_in_tile, half * 4 + j)) = pk;
                 }
               } else {
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < t.ncols) dst[j] = v[j] + rsd[j];
-              }
-            } else {
-              if (full) {
+                // staging holds [64 channels][128 tokens] as two 64-token boxes of 64 rows x 128 B
+                uint8_t* bx = eb + (row_in_tile >> 6) * 8192;
+                const uint32_t tl = row_in_tile & 63;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < t.ncols) dst[j] = v[j];
+                for (int j = 0; j < 32; ++j) {
+                  const uint32_t c = half * 32 + j;
+                  *reinterpret_cast<__nv_bfloat16*>(bx + c * 128 + ((((tl >> 3) ^ (c & 7)) << 4) | ((tl & 7) << 1))) =
+                      __float2bfloat16(v[j]);
+                }
               }
+            }
+          }
+          fence_proxy_async_smem();
+          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (leader) {
+            if (e_layout == LAYOUT_TOKEN) {
+              tma_store_3d(&tmC, eb, col0 + cc * CW, mt * GEMM_BM, b);
+            } else {
+              tma_store_3d(&tmC, eb, mt * GEMM_BM, col0 + cc * 64, b);
+              tma_store_3d(&tmC, eb + 8192, mt * GEMM_BM + 64, col0 + cc * 64, b);
+            }
+            tma_store_commit();
+            tma_store_wait_read<1>();                       // this group's previous store (chunk ec-2) has drained its buffer
+            if (ec >= 2) mbar_arrive(&eempty_bar[(ec - 2) % EPI_BUFS]);
+          }
+        }
+      } else if (grp == 0) {
+        // ------------------------- direct global stores (fallback, one group) -------------------------
+        long long cm_off = 0;
+        if (e_layout == LAYOUT_CHANNEL) cm_off = static_cast<long long>(row / p.cm_inner) * p.cm_pitch + row % p.cm_inner;
+#pragma unroll 1
+        for (int c0 = 0; c0 < W; c0 += 32) {
+          if (c0 >= ncols) break;           // warp-uniform
+          float v[32];
+          epi_values<BN, EK>(t_acc, c0, e_mode, e_act, bias_tile, rs, v);
+          if (!row_ok) continue;
+          if (!out_f32) {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t.out) + b * p.out_batch_stride;
+            if (e_layout == LAYOUT_TOKEN) {
+              __nv_bfloat16* dst = out + static_cast<long long>(row) * t.ld + col0 + c0;
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < ncols) dst[j] = __float2bfloat16(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < ncols) out[static_cast<long long>(col0 + c0 + j) * t.ld + cm_off] = __float2bfloat16(v[j]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(t.out) + b * p.out_batch_stride + static_cast<long long>(row) * t.ld + col0 + c0;
+            if (e_mode == EPI_RESID_F32) {
+              const float* rsd = p.resid + static_cast<long long>(row) * p.ld_resid + col0 + c0;
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < ncols) dst[j] = v[j] + rsd[j];
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < ncols) dst[j] = v[j];
             }
           }
         }
       }
-      // accumulator drained: hand the TMEM stage back to the MMA warp
+      // accumulator drained: hand the TMEM stage back to the MMA warp (8 warps arrive)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (!p.direct && leader) tma_store_wait_read<0>();   // smem must outlive the last TMA store's reads
   }
 
   tc_fence_before();

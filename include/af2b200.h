@@ -33,6 +33,14 @@ int af2_abi_version(void);
 /* 0 if the current device is compute capability 10.x, AF2_ERR_UNSUPPORTED_DEVICE otherwise */
 int af2_check_device(void);
 
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+unsigned long long af2_launch_count(void);
+/* Optional CUDA-event profiling per kernel class (0 linear GEMM, 1 per-channel GEMM, 2 attention, 3 LayerNorm,
+ * 4 channel->token, 5 misc): enable(1) clears the records; read() synchronises and sums elapsed ms, algorithmic
+ * FLOPs and bytes of the recorded launches of one class and returns their count. */
+void af2_profile_enable(int on);
+long long af2_profile_read(int cls, double* ms, double* flops, double* bytes);
+
 /* ---------------- FeedForward: alphafold2.py:74-94 (+ residual of :439 / :444) -----------------------
  * x <- x + W2 (a * gelu_erf(g)) + b2,  [a|g] = W1 LN(x) + b1.
  * w1 is packed per column tile of `bn` accumulator columns as [bn/2 value rows | bn/2 gate rows]
