@@ -332,7 +332,7 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
-  kern<<<grid, 192, L::TOTAL, s>>>(tq, tk, tv, tbias, p);
+  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }

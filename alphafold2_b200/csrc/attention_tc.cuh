@@ -4,11 +4,14 @@
 // One CTA = one (folded batch element b', head h, block of 128 queries).  Keys/values are streamed in
 // blocks of 128 through a 2-stage TMA pipeline together with the matching [128 q x 128 k] bf16 bias tile.
 //   S_j = Q K_j^T           tcgen05.mma  (M=128, N=128, K=DH)  -> TMEM (double buffered, 2 x 128 cols)
-//   softmax warps (4)       TMEM -> regs, + bias + mask, online max/sum, P_j -> smem (bf16, 128B swizzle),
-//                           rescale O in TMEM when the running max moves
+//   softmax warps (8)       two threads per query row (each owns 64 of the 128 keys of the block):
+//                           TMEM -> regs, + bias + key mask, online max/sum (row max exchanged through smem),
+//                           P_j -> smem (bf16, 128B swizzle), rescale O in TMEM when the running max moves
 //   O  += P_j V_j           tcgen05.mma  (M=128, N=DH, K=128), V consumed MN-major straight from its
 //                           [key][dh] layout
 //   epilogue                O / l * sigmoid-gate -> bf16 [token, h*DH + e]
+// Logits are produced directly in the log2 domain: the host folds dim_head^-0.5 * log2(e) into to_q and
+// log2(e) into edges_to_attn_bias, so the softmax is exp2(v - max) with no per-element scaling.
 //
 // Mask semantics (quirk Q1): logits where !(mask[q] & mask[k]) are REPLACED by -FLT_MAX.  For an unmasked
 // query that gives probability exactly 0 on masked keys; for a masked query every logit is equal, i.e. a
@@ -31,6 +34,8 @@ struct AttnParams {
   long long ld_gate, ld_out;
 };
 
+constexpr int ATTN_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
+
 template <int DH>
 struct AttnSmem {
   static constexpr int Q_BYTES = 128 * DH * 2;
@@ -43,14 +48,16 @@ struct AttnSmem {
   static constexpr int STAGE_OFF = Q_BYTES;
   static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
-  static constexpr int KB_OFF = BAR_OFF + 128;          // float key bias (0 / -inf), one per key of the current block pair
-  static constexpr int TOTAL = KB_OFF + 2 * 128 * 4 + 1024;
+  static constexpr int KB_OFF = BAR_OFF + 128;          // float key term (0 / -inf) [2][128]
+  static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
+  static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
+  static constexpr int TOTAL = L_OFF + 2 * 128 * 4 + 1024;
 };
 
 // tmQ/tmK/tmV: 4-D maps over the projection buffer, dims (e [DH], i [n], h [heads], b' [nbatch]),
 // box (DH, 128, 1, 1), swizzle = DH*2 bytes.  tmBias: 3-D (k [npad], q [n], h), box (64, 128, 1), SW128.
 template <int DH>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
                     const __grid_constant__ AttnParams p) {
@@ -70,6 +77,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* pv_done = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
+  float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
+  float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,9 +96,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
+      mbar_init(&s_empty[s], 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -166,107 +175,116 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ================================ softmax + epilogue (warps 2..5) ==============
-    const int q = warp & 3;
+    // ================================ softmax + epilogue (warps 2..9) ==============
+    const int q = warp & 3;               // TMEM lane quarter
+    const int hk = (warp - 2) >> 2;       // which 64-key half of every 128-key block this thread owns
     const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
     const int qi = q0 + r;
     const bool q_in = qi < p.n;
     bool q_valid = true;
     if (p.mask && q_in) q_valid = p.mask[b * p.mask_sb + qi * p.mask_si] != 0;
-    const int sm_tid = threadIdx.x - 64;  // 0..127
+    const int sm_tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    constexpr float LOG2E = 1.4426950408889634f;
     const float NEG_INF = -__int_as_float(0x7f800000);
+    constexpr bool O_OWNER_ALL = (DH == 64);     // DH=64: each half owns 32 O columns; DH=32: half 0 owns all 32
+    const bool o_owner = O_OWNER_ALL || hk == 0;
+    const uint32_t o_col = O_COL + (O_OWNER_ALL ? hk * 32 : 0);
 
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int st = j & 1;
-      // per-key additive term for this block (0 = usable key, -inf = masked or beyond n); slot st is safe to
-      // rewrite: its previous readers (block j-2) passed the named barrier of block j-1 before we got here.
-      {
+      // per-key additive term for this block (0 = usable key, -inf = masked or beyond n); slot st was last read
+      // two blocks ago and every thread has passed two named barriers since.
+      if (sm_tid < 128) {
         const int kidx = j * 128 + sm_tid;
         float kb = NEG_INF;
         if (kidx < p.n) kb = (!p.mask || p.mask[b * p.mask_sb + kidx * p.mask_si]) ? 0.f : NEG_INF;
         keyb[st * 128 + sm_tid] = kb;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
 
-      float s[128];
+      float s[64];
       {
-        uint32_t u[32];
+        uint32_t u0[32], u1[32];
+        tmem_ld32(tmem_base + S_COL + st * 128 + hk * 64 + lane_sel, u0);
+        tmem_ld32(tmem_base + S_COL + st * 128 + hk * 64 + 32 + lane_sel, u1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32(tmem_base + S_COL + st * 128 + c * 32 + lane_sel, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(u0[i]);
+          s[32 + i] = __uint_as_float(u1[i]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
 
-      // logits (log2 domain) = (s + bias) * log2e + keyterm
-      const uint8_t* sbias = smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES + L::V_BYTES;
-      const float* kbs = keyb + st * 128;
-      float mx = NEG_INF;
+      // logits (log2 domain) = s + bias + keyterm
+      const uint8_t* sbias = smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES + L::V_BYTES + hk * 16384;
+      const float* kbs = keyb + st * 128 + hk * 64;
+      float mx0 = NEG_INF, mx1 = NEG_INF;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {        // 16 chunks of 8 keys
-        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < 8; ++c) {         // 8 chunks of 8 keys
         if (p.has_bias) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(sbias + (c >> 3) * 16384 + swz128_off(r, c & 7));
-          bv[0] = bf16lo_to_f32(raw.x); bv[1] = bf16hi_to_f32(raw.x);
-          bv[2] = bf16lo_to_f32(raw.y); bv[3] = bf16hi_to_f32(raw.y);
-          bv[4] = bf16lo_to_f32(raw.z); bv[5] = bf16hi_to_f32(raw.z);
-          bv[6] = bf16lo_to_f32(raw.w); bv[7] = bf16hi_to_f32(raw.w);
+          const uint4 raw = *reinterpret_cast<const uint4*>(sbias + swz128_off(r, c));
+          s[c * 8 + 0] += bf16lo_to_f32(raw.x); s[c * 8 + 1] += bf16hi_to_f32(raw.x);
+          s[c * 8 + 2] += bf16lo_to_f32(raw.y); s[c * 8 + 3] += bf16hi_to_f32(raw.y);
+          s[c * 8 + 4] += bf16lo_to_f32(raw.z); s[c * 8 + 5] += bf16hi_to_f32(raw.z);
+          s[c * 8 + 6] += bf16lo_to_f32(raw.w); s[c * 8 + 7] += bf16hi_to_f32(raw.w);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = c * 8 + i;
-          const float kb = kbs[k];
-          const bool in_range = (j * 128 + k) < p.n;
-          float v = q_valid ? ((s[k] + bv[i]) * LOG2E + kb) : (in_range ? 0.f : NEG_INF);
-          s[k] = v;
-          mx = fmaxf(mx, v);
-        }
+        const float4 k0 = *reinterpret_cast<const float4*>(kbs + c * 8);
+        const float4 k1 = *reinterpret_cast<const float4*>(kbs + c * 8 + 4);
+        s[c * 8 + 0] += k0.x; s[c * 8 + 1] += k0.y; s[c * 8 + 2] += k0.z; s[c * 8 + 3] += k0.w;
+        s[c * 8 + 4] += k1.x; s[c * 8 + 5] += k1.y; s[c * 8 + 6] += k1.z; s[c * 8 + 7] += k1.w;
       }
-      const float m_new = fmaxf(m_run, mx);
+      if (!q_valid) {                        // rare: masked query row -> uniform over the n real keys
+#pragma unroll
+        for (int k = 0; k < 64; ++k) s[k] = (j * 128 + hk * 64 + k) < p.n ? 0.f : NEG_INF;
+      }
+#pragma unroll
+      for (int k = 0; k < 64; k += 2) {
+        mx0 = fmaxf(mx0, s[k]);
+        mx1 = fmaxf(mx1, s[k + 1]);
+      }
+      mxbuf[hk * 128 + r] = fmaxf(mx0, mx1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), mxbuf[(hk ^ 1) * 128 + r]));
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
       const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 128; ++k) {
-        const float e = fast_exp2(s[k] - m_use);
-        s[k] = e;
-        lsum += e;
+      for (int k = 0; k < 64; k += 2) {
+        const float e0 = fast_exp2(s[k] - m_use);
+        const float e1 = fast_exp2(s[k + 1] - m_use);
+        s[k] = e0; s[k + 1] = e1;
+        ls0 += e0; ls1 += e1;
       }
-      l_run = l_run * corr + lsum;
+      l_run = l_run * corr + (ls0 + ls1);
       m_run = m_new;
 
       // previous P V must be complete before O is rescaled and before P smem is overwritten
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        uint32_t o[32];
-#pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          tmem_ld32(tmem_base + O_COL + c * 32 + lane_sel, o);
+        if (o_owner) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + o_col + lane_sel, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-          tmem_st32(tmem_base + O_COL + c * 32 + lane_sel, o);
+          tmem_st32(tmem_base + o_col + lane_sel, o);
+          tmem_st_wait();
         }
-        tmem_st_wait();
       }
-      // P_j -> smem, bf16, K-major 128B swizzle (two 64-key chunks)
-      uint8_t* spb = smem + L::P_OFF;
+      // P_j -> smem, bf16, K-major 128B swizzle (this thread's 64-key chunk)
+      uint8_t* spb = smem + L::P_OFF + hk * 16384;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 8; ++c) {
         uint4 pk = make_uint4(pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]), pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]),
                               pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]), pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
-        *reinterpret_cast<uint4*>(spb + (c >> 3) * 16384 + swz128_off(r, c & 7)) = pk;
+        *reinterpret_cast<uint4*>(spb + swz128_off(r, c)) = pk;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -275,21 +293,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 
     // ---- epilogue: O / l * gate -> out ----
+    lbuf[hk * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv_l = 1.0f / (l_run + lbuf[(hk ^ 1) * 128 + r]);
     mbar_wait(pv_done, (nkv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
-    const __nv_bfloat16* gp = p.gate + tok * p.ld_gate + h * DH;
-    __nv_bfloat16* op = p.out + tok * p.ld_out + h * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
+    if (o_owner) {
+      const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
+      const int cbase = h * DH + (O_OWNER_ALL ? hk * 32 : 0);
+      const __nv_bfloat16* gp = p.gate + tok * p.ld_gate + cbase;
+      __nv_bfloat16* op = p.out + tok * p.ld_out + cbase;
       uint32_t o[32];
-      tmem_ld32(tmem_base + O_COL + c * 32 + lane_sel, o);
+      tmem_ld32(tmem_base + o_col + lane_sel, o);
       tmem_ld_wait();
       if (q_in) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          const uint4 g = *reinterpret_cast<const uint4*>(gp + c * 32 + i);
+          const uint4 g = *reinterpret_cast<const uint4*>(gp + i);
           const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
           uint32_t ow[4];
 #pragma unroll
@@ -298,7 +318,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float bb = __uint_as_float(o[i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
             ow[t] = pack_bf16x2(a, bb);
           }
-          *reinterpret_cast<uint4*>(op + c * 32 + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          *reinterpret_cast<uint4*>(op + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
     }

@@ -39,10 +39,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ float sigmoidf_fast(float x) {
   // 1 / (1 + 2^(-x log2 e)); ex2.approx + rcp.approx: rel. error ~1e-6, far inside bf16 rounding
-  return __frcp_rn(1.0f + fast_exp2(-1.4426950408889634f * x));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(-1.4426950408889634f * x)));
+  return r;
 }
+// exact (erf) GELU of F.gelu: erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the bf16 rounding of the
+// result) on the MUFU rcp / ex2 units instead of the branchy libdevice erff.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = fast_exp2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);                  // erf(|x|/sqrt2)
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -83,19 +83,44 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const LnParams p) {
     }
     if (p.wb) {
       const long long off = (t / p.n_inner) * p.pitch + (t % p.n_inner);
-      for (int h = 0; h < p.heads; ++h) {
-        const float4* wr = reinterpret_cast<const float4*>(p.wb + static_cast<long long>(h) * p.d);
-        float acc = 0.f;
+      // 8 heads at a time: per-lane partial dot products, then a recursive-halving butterfly (9 shuffles for 8
+      // sums instead of 40): after the xor-16/8/4 steps lane l holds head ((l>>2)&7)'s partial, xor-2/1 finish it.
+      for (int h0 = 0; h0 < p.heads; h0 += 8) {
+        float acc[8];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          const int idx = lane + 32 * c;
-          if (idx < nchunk) {
-            const float4 w = __ldg(wr + idx);
-            acc += v[c].x * w.x + v[c].y * w.y + v[c].z * w.z + v[c].w * w.w;
+        for (int hh = 0; hh < 8; ++hh) {
+          acc[hh] = 0.f;
+          if (h0 + hh < p.heads) {
+            const float4* wr = reinterpret_cast<const float4*>(p.wb + static_cast<long long>(h0 + hh) * p.d);
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+              const int idx = lane + 32 * c;
+              if (idx < nchunk) {
+                const float4 w = __ldg(wr + idx);
+                acc[hh] += v[c].x * w.x + v[c].y * w.y + v[c].z * w.z + v[c].w * w.w;
+              }
+            }
           }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) p.bias_out[h * p.bias_hs + off] = __float2bfloat16(acc);
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float w4[4], w2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float mine = b4 ? acc[4 + i] : acc[i];
+          const float other = b4 ? acc[i] : acc[4 + i];
+          w4[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float mine = b3 ? w4[2 + i] : w4[i];
+          const float other = b3 ? w4[i] : w4[2 + i];
+          w2[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+        }
+        float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+        const int hsel = h0 + ((lane >> 2) & 7);
+        if ((lane & 3) == 0 && hsel < p.heads) p.bias_out[hsel * p.bias_hs + off] = __float2bfloat16(w1);
       }
     }
   }

@@ -110,11 +110,14 @@ def pack_feed_forward(norm_w, norm_b, w1, b1, w2, b2) -> Packed:
 
 
 def pack_attention(norm_w, norm_b, wq, wkv, wg, bg, wo, bo, w_edge, dim_head: int) -> Packed:
-    scale = dim_head ** -0.5                                  # alphafold2.py:112,138 folded into to_q
+    # alphafold2.py:112,138: q * dim_head^-0.5 is folded into to_q, together with log2(e) so that the kernel's
+    # softmax works in the exp2 domain; the pair-bias projection gets the same log2(e).
+    log2e = 1.4426950408889634
+    scale = dim_head ** -0.5 * log2e
     wqkv = torch.cat([wq.detach().float() * scale, wkv.detach().float()], dim=0)
     t = dict(g=_f32(norm_w), b=_f32(norm_b), wqkv=_bf16(wqkv), wg=_bf16(wg), bg=_f32(bg), wo=_bf16(wo), bo=_f32(bo))
     if w_edge is not None:
-        t["we"] = _f32(w_edge)
+        t["we"] = _f32(w_edge.detach().float() * log2e)
     s = _lib.AttnWeights(t["g"].data_ptr(), t["b"].data_ptr(), t["wqkv"].data_ptr(), t["wg"].data_ptr(),
                          t["bg"].data_ptr(), t["wo"].data_ptr(), t["bo"].data_ptr(),
                          t["we"].data_ptr() if w_edge is not None else None)
