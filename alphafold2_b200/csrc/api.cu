@@ -328,7 +328,9 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  dim3 grid((p.n + 127) / 128, p.heads, p.nbatch);
+  const long long items = (long long)((p.n + 127) / 128) * p.heads * p.nbatch;
+  if (items <= 0) return AF2_OK;
+  const int grid = (int)(items < sm_count() ? items : sm_count());     // persistent CTAs
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));

@@ -1,8 +1,10 @@
 // Axial self-attention with shared additive pair bias and the reference's two-sided mask, on tcgen05.
 // Replaces Attention.forward (alphafold2.py:125-190) as driven by AxialAttention (alphafold2.py:219-255).
 //
-// One CTA = one (folded batch element b', head h, block of 128 queries).  Keys/values are streamed in
-// blocks of 128 through a 2-stage TMA pipeline together with the matching [128 q x 128 k] bf16 bias tile.
+// Persistent CTAs; a work item = one (folded batch element b', head h, block of 128 queries), ordered so that
+// concurrently running CTAs share the same (h, query block) bias tiles in L2.  Keys/values are streamed in
+// blocks of 128 through a 2-stage TMA pipeline together with the matching [128 q x 128 k] bf16 bias tile; the
+// producer runs ahead across work items (Q is double buffered), so loads of item i+1 overlap the math of item i.
 //   S_j = Q K_j^T           tcgen05.mma  (M=128, N=128, K=DH)  -> TMEM (double buffered, 2 x 128 cols)
 //   softmax warps (8)       two threads per query row (each owns 64 of the 128 keys of the block):
 //                           TMEM -> regs, + bias + key mask, online max/sum (row max exchanged through smem),
@@ -44,8 +46,8 @@ struct AttnSmem {
   static constexpr int BIAS_BYTES = 128 * 128 * 2;      // two 64-key boxes of [128 q rows x 128 B]
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BIAS_BYTES;
   static constexpr int P_BYTES = 128 * 128 * 2;         // two 64-key K-chunks of [128 q rows x 128 B]
-  static constexpr int Q_OFF = 0;
-  static constexpr int STAGE_OFF = Q_BYTES;
+  static constexpr int Q_OFF = 0;                       // [2] Q buffers
+  static constexpr int STAGE_OFF = 2 * Q_BYTES;
   static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
   static constexpr int KB_OFF = BAR_OFF + 128;          // float key term (0 / -inf) [2][128]
@@ -68,31 +70,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* s_empty = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* pv_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;     // [2]
+  uint64_t* s_empty = bars + 10;   // [2]
+  uint64_t* p_full = bars + 12;
+  uint64_t* pv_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
   float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * 128;
   const int nkv = (p.n + 127) / 128;
+  const int nqb = nkv;
+  const int total_items = nqb * p.heads * p.nbatch;
+  const int my_items = (total_items > static_cast<int>(blockIdx.x))
+                           ? (total_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  // item id = ((h * nqb + qb) * nbatch + b'): neighbours in time differ only in b' and share the bias tile
+  auto decode = [&](int it, int& qb_, int& h_, int& b_) {
+    const int id = blockIdx.x + it * gridDim.x;
+    b_ = id % p.nbatch;
+    qb_ = (id / p.nbatch) % nqb;
+    h_ = id / (p.nbatch * nqb);
+  };
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0, O_COL = 256;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     if (p.has_bias) prefetch_tmap(&tmBias);
-    mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
@@ -111,21 +124,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-      tma_load_4d(smem + L::Q_OFF, &tmQ, q_full, 0, q0, h, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        uint8_t* sk = smem + L::STAGE_OFF + st * L::STAGE_BYTES;
-        uint8_t* sv = sk + L::K_BYTES;
-        uint8_t* sbias = sv + L::V_BYTES;
-        mbar_arrive_expect_tx(&kv_full[st], L::K_BYTES + L::V_BYTES + (p.has_bias ? L::BIAS_BYTES : 0));
-        tma_load_4d(sk, &tmK, &kv_full[st], 0, j * 128, h, b);
-        tma_load_4d(sv, &tmV, &kv_full[st], 0, j * 128, h, b);
-        if (p.has_bias) {
-          tma_load_3d(sbias, &tmBias, &kv_full[st], j * 128, q0, h);
-          tma_load_3d(sbias + 16384, &tmBias, &kv_full[st], j * 128 + 64, q0, h);
+      for (int it = 0; it < my_items; ++it) {
+        int qb, h, b;
+        decode(it, qb, h, b);
+        const int qs = it & 1;
+        mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qs], L::Q_BYTES);
+        tma_load_4d(smem + L::Q_OFF + qs * L::Q_BYTES, &tmQ, &q_full[qs], 0, qb * 128, h, b);
+        for (int j = 0; j < nkv; ++j) {
+          const int g = it * nkv + j;
+          const int st = g & 1;
+          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          uint8_t* sk = smem + L::STAGE_OFF + st * L::STAGE_BYTES;
+          uint8_t* sv = sk + L::K_BYTES;
+          uint8_t* sbias = sv + L::V_BYTES;
+          mbar_arrive_expect_tx(&kv_full[st], L::K_BYTES + L::V_BYTES + (p.has_bias ? L::BIAS_BYTES : 0));
+          tma_load_4d(sk, &tmK, &kv_full[st], 0, j * 128, h, b);
+          tma_load_4d(sv, &tmV, &kv_full[st], 0, j * 128, h, b);
+          if (p.has_bias) {
+            tma_load_3d(sbias, &tmBias, &kv_full[st], j * 128, qb * 128, h);
+            tma_load_3d(sbias + 16384, &tmBias, &kv_full[st], j * 128 + 64, qb * 128, h);
+          }
         }
       }
     }
@@ -133,14 +152,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ================================ MMA issuer ==================================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, V is MN-major
-    const uint32_t sq = smem_u32(smem + L::Q_OFF);
     const uint32_t sp = smem_u32(smem + L::P_OFF);
-    auto issue_s = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
-      mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
+    const int total_blocks = my_items * nkv;
+    auto issue_s = [&](int g) {
+      const int it = g / nkv, j = g - it * nkv;
+      const int qs = it & 1, st = g & 1;
+      if (j == 0) mbar_wait(&q_full[qs], (it >> 1) & 1);
+      mbar_wait(&kv_full[st], (g >> 1) & 1);
+      mbar_wait(&s_empty[st], ((g >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
+        const uint32_t sq = smem_u32(smem + L::Q_OFF + qs * L::Q_BYTES);
         const uint32_t sk = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -149,25 +171,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[st]);
+        if (j == nkv - 1) umma_commit(&q_empty[qs]);     // Q buffer reusable once the item's last QK^T retires
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j & 1;
-      if (j + 1 < nkv) issue_s(j + 1);
-      mbar_wait(p_full, j & 1);
+    if (total_blocks > 0) issue_s(0);
+    for (int g = 0; g < total_blocks; ++g) {
+      const int st = g & 1;
+      if (g + 1 < total_blocks) issue_s(g + 1);
+      mbar_wait(p_full, g & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sv = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES);
+        const bool first = (g % nkv) == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A = P: two 64-key chunks of 16 KB, K step 32 B inside a chunk
           const uint64_t ad = umma_smem_desc(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128);
           // B = V [key][dh], MN-major: 16 keys = 2 swizzle atoms of 8 key-rows
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
-          umma_bf16(tmem_base + O_COL, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + O_COL, ad, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
         }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
@@ -179,10 +202,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;               // TMEM lane quarter
     const int hk = (warp - 2) >> 2;       // which 64-key half of every 128-key block this thread owns
     const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
-    const int qi = q0 + r;
-    const bool q_in = qi < p.n;
-    bool q_valid = true;
-    if (p.mask && q_in) q_valid = p.mask[b * p.mask_sb + qi * p.mask_si] != 0;
     const int sm_tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const float NEG_INF = -__int_as_float(0x7f800000);
@@ -190,9 +209,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool o_owner = O_OWNER_ALL || hk == 0;
     const uint32_t o_col = O_COL + (O_OWNER_ALL ? hk * 32 : 0);
 
+    for (int it = 0; it < my_items; ++it) {
+    int qb, h, b;
+    decode(it, qb, h, b);
+    const int qi = qb * 128 + r;
+    const bool q_in = qi < p.n;
+    bool q_valid = true;
+    if (p.mask && q_in) q_valid = p.mask[b * p.mask_sb + qi * p.mask_si] != 0;
+
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int st = j & 1;
+      const int g = it * nkv + j;
+      const int st = g & 1;
       // per-key additive term for this block (0 = usable key, -inf = masked or beyond n); slot st was last read
       // two blocks ago and every thread has passed two named barriers since.
       if (sm_tid < 128) {
@@ -202,7 +230,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         keyb[st * 128 + sm_tid] = kb;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&s_full[st], (j >> 1) & 1);
+      mbar_wait(&s_full[st], (g >> 1) & 1);
       tc_fence_after();
 
       float s[64];
@@ -266,7 +294,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
       // previous P V must be complete before O is rescaled and before P smem is overwritten
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (g - 1) & 1);
         tc_fence_after();
         if (o_owner) {
           uint32_t o[32];
@@ -296,7 +324,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     lbuf[hk * 128 + r] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float inv_l = 1.0f / (l_run + lbuf[(hk ^ 1) * 128 + r]);
-    mbar_wait(pv_done, (nkv - 1) & 1);
+    mbar_wait(pv_done, (it * nkv + nkv - 1) & 1);
     tc_fence_after();
     if (o_owner) {
       const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
@@ -322,6 +350,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
+    tc_fence_before();            // O has been read: order it before the next item's first P V
+    }  // work items
   }
 
   tc_fence_before();
