@@ -320,7 +320,7 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
 // -------------------------------------------------------------------------------------------------
 template <int DH>
 int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
-                          const AttnParams& p, cudaStream_t s) {
+                          const CUtensorMap& tg, const AttnParams& p, cudaStream_t s) {
   using L = AttnSmem<DH>;
   static bool configured = false;
   auto kern = attention_tc_kernel<DH>;
@@ -334,7 +334,7 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
-  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, p);
+  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }
@@ -345,7 +345,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
                      __nv_bfloat16* out, cudaStream_t s) {
   const long long I = (long long)heads * dh;
   const long long ld = 3 * I;
-  CUtensorMap tq, tk, tv, tb;
+  CUtensorMap tq, tk, tv, tb, tg;
   unsigned long long dims[4] = {(unsigned long long)dh, (unsigned long long)n, (unsigned long long)heads, (unsigned long long)nbatch};
   unsigned long long str[3] = {(unsigned long long)(tok_si * ld * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * ld * 2)};
   unsigned box[4] = {(unsigned)dh, 128, 1, 1};
@@ -353,6 +353,8 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz));
   AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz));
   AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz));
+  unsigned long long gstr[3] = {(unsigned long long)(tok_si * I * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * I * 2)};
+  AF2_TRY(make_tmap(&tg, gate, 4, dims, gstr, box, swz));
   if (bias) {
     unsigned long long bd[3] = {(unsigned long long)npad, (unsigned long long)n, (unsigned long long)heads};
     unsigned long long bs[2] = {(unsigned long long)npad * 2, (unsigned long long)n * npad * 2};
@@ -366,8 +368,8 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.n = n; p.heads = heads; p.nbatch = nbatch; p.has_bias = bias != nullptr;
   p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
   p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
-  if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, p, s);
-  if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, p, s);
+  if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, p, s);
+  if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, p, s);
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
 }
 

@@ -36,7 +36,7 @@ struct AttnParams {
   long long ld_gate, ld_out;
 };
 
-constexpr int ATTN_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
+constexpr int ATTN_THREADS = 352;   // TMA warp, MMA warp, 8 softmax warps, key-mask warp
 
 template <int DH>
 struct AttnSmem {
@@ -46,14 +46,16 @@ struct AttnSmem {
   static constexpr int BIAS_BYTES = 128 * 128 * 2;      // two 64-key boxes of [128 q rows x 128 B]
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BIAS_BYTES;
   static constexpr int P_BYTES = 128 * 128 * 2;         // two 64-key K-chunks of [128 q rows x 128 B]
-  static constexpr int Q_OFF = 0;                       // [2] Q buffers
-  static constexpr int STAGE_OFF = 2 * Q_BYTES;
+  static constexpr int Q_OFF = 0;                       // Q tile of the current item
+  static constexpr int G_OFF = Q_BYTES;                 // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
+  static constexpr int STAGE_OFF = 3 * Q_BYTES;
   static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
-  static constexpr int KB_OFF = BAR_OFF + 128;          // float key term (0 / -inf) [2][128]
+  static constexpr int KB_OFF = BAR_OFF + 256;          // float key term (0 / -inf) [2][128]
   static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
   static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
-  static constexpr int TOTAL = L_OFF + 2 * 128 * 4 + 1024;
+  static constexpr int QV_OFF = L_OFF + 2 * 128 * 4;    // query-mask bytes [2][128]
+  static constexpr int TOTAL = QV_OFF + 2 * 128 + 1024;
 };
 
 // tmQ/tmK/tmV: 4-D maps over the projection buffer, dims (e [DH], i [n], h [heads], b' [nbatch]),
@@ -62,7 +64,7 @@ template <int DH>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
-                    const __grid_constant__ AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmG, const __grid_constant__ AttnParams p) {
   using L = AttnSmem<DH>;
   constexpr uint32_t SWZ = (DH == 64) ? SWZ_128 : SWZ_64;
   constexpr uint32_t ROWB = DH * 2;                 // bytes per Q/K/V row
@@ -70,18 +72,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* q_full = bars + 0;     // [2]
-  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* q_full = bars + 0;     // Q tile landed
+  uint64_t* g_full = bars + 1;     // [2] gate tile landed (slot it & 1)
+  uint64_t* q_empty = bars + 3;    // Q tile consumed by the item's last QK^T
   uint64_t* kv_full = bars + 4;    // [2]
   uint64_t* kv_empty = bars + 6;   // [2]
   uint64_t* s_full = bars + 8;     // [2]
   uint64_t* s_empty = bars + 10;   // [2]
   uint64_t* p_full = bars + 12;
   uint64_t* pv_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kb_full = bars + 14;   // [2] key-mask terms of a block staged
+  uint64_t* kb_empty = bars + 16;  // [2] ... and consumed by the 8 softmax warps
+  uint64_t* g_empty = bars + 18;   // [2] gate tile consumed by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
   float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
+  uint8_t* qvbuf = smem + L::QV_OFF;                          // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,15 +108,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t S_COL = 0, O_COL = 256;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmG);
     if (p.has_bias) prefetch_tmap(&tmBias);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&q_full[s], 1);
-      mbar_init(&q_empty[s], 1);
+      mbar_init(&g_full[s], 1);
+      mbar_init(&g_empty[s], 8);
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 8);
+      mbar_init(&kb_full[s], 1);
+      mbar_init(&kb_empty[s], 8);
     }
     mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
@@ -127,10 +138,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
         decode(it, qb, h, b);
-        const int qs = it & 1;
-        mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qs], L::Q_BYTES);
-        tma_load_4d(smem + L::Q_OFF + qs * L::Q_BYTES, &tmQ, &q_full[qs], 0, qb * 128, h, b);
+        const int gs = it & 1;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+        tma_load_4d(smem + L::Q_OFF, &tmQ, q_full, 0, qb * 128, h, b);
+        mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
+        tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
           const int st = g & 1;
@@ -156,13 +170,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int total_blocks = my_items * nkv;
     auto issue_s = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
-      const int qs = it & 1, st = g & 1;
-      if (j == 0) mbar_wait(&q_full[qs], (it >> 1) & 1);
+      const int st = g & 1;
+      if (j == 0) mbar_wait(q_full, it & 1);
       mbar_wait(&kv_full[st], (g >> 1) & 1);
       mbar_wait(&s_empty[st], ((g >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sq = smem_u32(smem + L::Q_OFF + qs * L::Q_BYTES);
+        const uint32_t sq = smem_u32(smem + L::Q_OFF);
         const uint32_t sk = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -171,7 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[st]);
-        if (j == nkv - 1) umma_commit(&q_empty[qs]);     // Q buffer reusable once the item's last QK^T retires
+        if (j == nkv - 1) umma_commit(q_empty);          // Q buffer reusable once the item's last QK^T retires
       }
       __syncwarp();
     };
@@ -197,12 +211,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     }
+  } else if (warp == 10) {
+    // ================================ key-mask warp ================================
+    // stages, one block ahead of the softmax warps, the additive key term of every 128-key block:
+    // 0 = usable key, -inf = masked key or tile padding beyond n (hides the mask's global-load latency)
+    const float NEG_INF = -__int_as_float(0x7f800000);
+    for (int it = 0; it < my_items; ++it) {
+      int qb, h, b;
+      decode(it, qb, h, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int g = it * nkv + j;
+        const int st = g & 1;
+        float kb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kidx = j * 128 + lane * 4 + i;
+          kb[i] = NEG_INF;
+          if (kidx < p.n) kb[i] = (!p.mask || p.mask[b * p.mask_sb + kidx * p.mask_si]) ? 0.f : NEG_INF;
+        }
+        uint32_t qv = 0x01010101u;
+        if (j == 0 && p.mask) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qi = qb * 128 + lane * 4 + i;
+            if (qi < p.n && p.mask[b * p.mask_sb + qi * p.mask_si] == 0) qv &= ~(0xffu << (8 * i));
+          }
+        }
+        mbar_wait(&kb_empty[st], ((g >> 1) & 1) ^ 1);
+        *reinterpret_cast<float4*>(keyb + st * 128 + lane * 4) = make_float4(kb[0], kb[1], kb[2], kb[3]);
+        if (j == 0) *reinterpret_cast<uint32_t*>(qvbuf + (it & 1) * 128 + lane * 4) = qv;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&kb_full[st]);
+      }
+    }
   } else {
     // ================================ softmax + epilogue (warps 2..9) ==============
     const int q = warp & 3;               // TMEM lane quarter
     const int hk = (warp - 2) >> 2;       // which 64-key half of every 128-key block this thread owns
     const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
-    const int sm_tid = threadIdx.x - 64;  // 0..255
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const float NEG_INF = -__int_as_float(0x7f800000);
     constexpr bool O_OWNER_ALL = (DH == 64);     // DH=64: each half owns 32 O columns; DH=32: half 0 owns all 32
@@ -215,21 +261,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int qi = qb * 128 + r;
     const bool q_in = qi < p.n;
     bool q_valid = true;
-    if (p.mask && q_in) q_valid = p.mask[b * p.mask_sb + qi * p.mask_si] != 0;
 
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int g = it * nkv + j;
       const int st = g & 1;
-      // per-key additive term for this block (0 = usable key, -inf = masked or beyond n); slot st was last read
-      // two blocks ago and every thread has passed two named barriers since.
-      if (sm_tid < 128) {
-        const int kidx = j * 128 + sm_tid;
-        float kb = NEG_INF;
-        if (kidx < p.n) kb = (!p.mask || p.mask[b * p.mask_sb + kidx * p.mask_si]) ? 0.f : NEG_INF;
-        keyb[st * 128 + sm_tid] = kb;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&kb_full[st], (g >> 1) & 1);      // key terms (and, at j == 0, query-mask bytes) staged by the key-mask warp
+      if (j == 0) q_valid = qvbuf[(it & 1) * 128 + r] != 0;
       mbar_wait(&s_full[st], (g >> 1) & 1);
       tc_fence_after();
 
@@ -267,6 +305,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         s[c * 8 + 0] += k0.x; s[c * 8 + 1] += k0.y; s[c * 8 + 2] += k0.z; s[c * 8 + 3] += k0.w;
         s[c * 8 + 4] += k1.x; s[c * 8 + 5] += k1.y; s[c * 8 + 6] += k1.z; s[c * 8 + 7] += k1.w;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&kb_empty[st]);
       if (!q_valid) {                        // rare: masked query row -> uniform over the n real keys
 #pragma unroll
         for (int k = 0; k < 64; ++k) s[k] = (j * 128 + hk * 64 + k) < p.n ? 0.f : NEG_INF;
@@ -277,7 +317,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx1 = fmaxf(mx1, s[k + 1]);
       }
       mxbuf[hk * 128 + r] = fmaxf(mx0, mx1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // only the two warps sharing these 32 rows
       const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), mxbuf[(hk ^ 1) * 128 + r]));
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
       const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
@@ -322,34 +362,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     // ---- epilogue: O / l * gate -> out ----
     lbuf[hk * 128 + r] = l_run;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     const float inv_l = 1.0f / (l_run + lbuf[(hk ^ 1) * 128 + r]);
     mbar_wait(pv_done, (it * nkv + nkv - 1) & 1);
     tc_fence_after();
+    mbar_wait(&g_full[it & 1], (it >> 1) & 1);
     if (o_owner) {
       const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
       const int cbase = h * DH + (O_OWNER_ALL ? hk * 32 : 0);
-      const __nv_bfloat16* gp = p.gate + tok * p.ld_gate + cbase;
       __nv_bfloat16* op = p.out + tok * p.ld_out + cbase;
+      const uint8_t* gt = smem + L::G_OFF + (it & 1) * L::Q_BYTES;
       uint32_t o[32];
       tmem_ld32(tmem_base + o_col + lane_sel, o);
       tmem_ld_wait();
-      if (q_in) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint4 g = *reinterpret_cast<const uint4*>(gp + i);
-          const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-          uint32_t ow[4];
+      for (int i = 0; i < 4; ++i) {
+        // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32)
+        const uint32_t goff = (DH == 64) ? swz128_off(r, hk * 4 + i) : (r * 64u + ((static_cast<uint32_t>(i) ^ ((r >> 1) & 3u)) << 4));
+        const uint4 gq = *reinterpret_cast<const uint4*>(gt + goff);
+        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+        uint32_t ow[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float a = __uint_as_float(o[i + 2 * t]) * inv_l * bf16lo_to_f32(gw[t]);
-            const float bb = __uint_as_float(o[i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
-            ow[t] = pack_bf16x2(a, bb);
-          }
-          *reinterpret_cast<uint4*>(op + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        for (int t = 0; t < 4; ++t) {
+          const float a = __uint_as_float(o[8 * i + 2 * t]) * inv_l * bf16lo_to_f32(gw[t]);
+          const float bb = __uint_as_float(o[8 * i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
+          ow[t] = pack_bf16x2(a, bb);
         }
+        if (q_in) *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&g_empty[it & 1]);
     tc_fence_before();            // O has been read: order it before the next item's first P V
     }  // work items
   }
