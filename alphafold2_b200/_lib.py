@@ -46,6 +46,16 @@ _SIGNATURES = {
     "af2_triangle_multiply_workspace": (ll, [ci, ci, ci]),
     "af2_outer_mean": (ci, [C.POINTER(OuterWeights), vp, vp, vp, ci, ci, ci, ci, cf, vp, ll, vp]),
     "af2_outer_mean_workspace": (ll, [ci, ci, ci, ci]),
+    "af2_pair_bias": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
+    "af2_axial_attention_prebias": (ci, [C.POINTER(AttnWeights), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_triangle_project": (ci, [C.POINTER(TriMulWeights), vp, vp, ll, ci, ci, vp, vp, ll, vp, vp, ll, vp]),
+    "af2_triangle_project_workspace": (ll, [ll, ci]),
+    "af2_triangle_contract": (ci, [C.POINTER(TriMulWeights), vp, vp, ll, vp, ll, ll, ci, vp, ci, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_triangle_contract_workspace": (ll, [ci, ci, ci]),
+    "af2_outer_project": (ci, [C.POINTER(OuterWeights), vp, vp, ll, ci, ci, vp, ll, vp, ll, vp]),
+    "af2_outer_project_workspace": (ll, [ll, ci]),
+    "af2_outer_contract": (ci, [C.POINTER(OuterWeights), vp, vp, ll, vp, ll, ll, ci, vp, ci, ci, ci, ci, ci, cf, vp, ll, vp]),
+    "af2_outer_contract_workspace": (ll, [ci, ci, ci]),
     "af2_rotary": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "af2_layernorm_bf16": (ci, [vp, vp, vp, vp, ll, ci, cf, vp]),
     "af2_gemm_bf16_f32": (ci, [vp, ll, ll, vp, ll, ll, vp, ll, ll, ci, ci, ci, ci, ci, vp]),

@@ -466,9 +466,9 @@ long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads
          align_up((long long)B * heads * n * npad * 2, 256) + 1024;
 }
 
-int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask, int B,
-                        int h, int wdim, int d, int heads, int dim_head, int row_attn, void* workspace,
-                        long long workspace_bytes, af2_stream_t stream) {
+static int axial_attention_impl(const af2_attn_weights* w, float* x, const float* edges, const void* pre_bias,
+                                const unsigned char* mask, int B, int h, int wdim, int d, int heads, int dim_head,
+                                int row_attn, void* workspace, long long workspace_bytes, af2_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x) return fail(AF2_ERR_BAD_ARG, "axial_attention: null argument");
   if (dim_head != 32 && dim_head != 64) return fail(AF2_ERR_BAD_ARG, "axial_attention: dim_head %d unsupported (32 or 64)", dim_head);
@@ -478,7 +478,7 @@ int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges,
   const int n = row_attn ? wdim : h;
   const int nb = row_attn ? h : wdim;
   const int npad = (int)align_up(n, 8);
-  const bool has_bias = edges != nullptr && w->w_edge != nullptr;
+  const bool has_bias = pre_bias != nullptr || (edges != nullptr && w->w_edge != nullptr);
   Arena ar(workspace, workspace_bytes);
   __nv_bfloat16* xn = ar.take<__nv_bfloat16>(T * d);
   __nv_bfloat16* qkv = ar.take<__nv_bfloat16>(T * 3 * I);
@@ -486,19 +486,20 @@ int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges,
   __nv_bfloat16* og = ar.take<__nv_bfloat16>(T * I);
   __nv_bfloat16* bias = ar.take<__nv_bfloat16>((long long)B * heads * n * npad);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "axial_attention: workspace too small");
+  if (pre_bias) bias = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(pre_bias));   // [B][H][n][npad], zero padded
 
   // 1. LayerNorm (+ pair bias from the RAW edges; fused when the edges are x itself)
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
-  const bool fuse_bias = has_bias && edges == x && B == 1;
+  const bool fuse_bias = has_bias && !pre_bias && edges == x && B == 1;
   // pad key columns are loaded by TMA next to valid ones: keep them finite (zero)
-  if (has_bias && npad != n) CUDA_OK(cudaMemsetAsync(bias, 0, (size_t)B * heads * n * npad * 2, s));
+  if (has_bias && !pre_bias && npad != n) CUDA_OK(cudaMemsetAsync(bias, 0, (size_t)B * heads * n * npad * 2, s));
   if (fuse_bias) {
     lp.wb = w->w_edge; lp.bias_out = bias; lp.heads = heads; lp.bias_hs = (long long)n * npad; lp.n_inner = n; lp.pitch = npad;
   }
   AF2_TRY(launch_layernorm(lp, s));
-  if (has_bias && !fuse_bias) {
+  if (has_bias && !fuse_bias && !pre_bias) {
     for (int b = 0; b < B; ++b) {
       LnParams bp;
       memset(&bp, 0, sizeof(bp));
@@ -671,6 +672,217 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   cp.scale = msa_mask ? scale : nullptr; cp.scale_const = 1.0f / (float)S; cp.y = tn;
   AF2_TRY(launch_chan_to_token(cp, s));
   GemmCall co = linear_call(tn, d, w->w_out, d, (int)Tx, d, d);
+  co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
+  AF2_TRY(launch_gemm(co, s));
+  return AF2_OK;
+}
+
+
+int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask, int B,
+                        int h, int wdim, int d, int heads, int dim_head, int row_attn, void* workspace,
+                        long long workspace_bytes, af2_stream_t stream) {
+  return axial_attention_impl(w, x, edges, nullptr, mask, B, h, wdim, d, heads, dim_head, row_attn, workspace,
+                              workspace_bytes, stream);
+}
+
+int af2_axial_attention_prebias(const af2_attn_weights* w, float* x, const void* bias_bf16, const unsigned char* mask,
+                                int B, int h, int wdim, int d, int heads, int dim_head, int row_attn, void* workspace,
+                                long long workspace_bytes, af2_stream_t stream) {
+  return axial_attention_impl(w, x, nullptr, bias_bf16, mask, B, h, wdim, d, heads, dim_head, row_attn, workspace,
+                              workspace_bytes, stream);
+}
+
+// bias rows of a shard of the pair tensor: out[h][r][j] (pitch npad, caller zero-fills the pad) = <x[r, j, :], w_edge[h, :]>
+int af2_pair_bias(const float* x_rows, const float* w_edge, void* bias_out, int rows, int n, int d, int heads,
+                  af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!x_rows || !w_edge || !bias_out) return fail(AF2_ERR_BAD_ARG, "pair_bias: null argument");
+  const int npad = (int)align_up(n, 8);
+  LnParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.x = x_rows; bp.T = (long long)rows * n; bp.d = d; bp.eps = 1e-5f;
+  bp.wb = w_edge; bp.bias_out = static_cast<__nv_bfloat16*>(bias_out); bp.heads = heads;
+  bp.bias_hs = (long long)rows * npad; bp.n_inner = n; bp.pitch = npad;
+  return launch_layernorm(bp, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level triangle multiply (used by the sharded path; pieces = number of gathered operand shards)
+// ------------------------------------------------------------------------------------------------
+long long af2_triangle_project_workspace(long long tokens, int d) {
+  return align_up(tokens * d * 2, 256) + align_up(tokens * 4, 256) + 1024;
+}
+
+int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsigned char* mask, long long tokens,
+                         int inner, int d, void* Lc, void* Rc, long long chan_stride, void* gate, void* workspace,
+                         long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x || !Lc || !Rc || !gate) return fail(AF2_ERR_BAD_ARG, "triangle_project: null argument");
+  if (d % 32) return fail(AF2_ERR_BAD_ARG, "triangle_project: dim %d must be a multiple of 32", d);
+  if (tokens % inner) return fail(AF2_ERR_BAD_ARG, "triangle_project: tokens must be a multiple of inner");
+  const int pitch = (int)align_up(inner, 8);
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* xn = ar.take<__nv_bfloat16>(tokens * d);
+  float* maskf = ar.take<float>(tokens);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_project: workspace too small");
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
+  AF2_TRY(launch_layernorm(lp, s));
+  if (mask) {
+    { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(tokens), 256, 0, s>>>(mask, maskf, tokens); }
+    CUDA_OK(cudaGetLastError());
+  }
+  if (pitch != inner) {
+    CUDA_OK(cudaMemsetAsync(Lc, 0, (size_t)d * chan_stride * 2, s));
+    CUDA_OK(cudaMemsetAsync(Rc, 0, (size_t)d * chan_stride * 2, s));
+  }
+  const int half = w->bn / 2;
+  const int npk = (d + half - 1) / half * w->bn;
+  for (int side = 0; side < 2; ++side) {
+    GemmCall c = linear_call(xn, d, side ? w->w_right : w->w_left, d, (int)tokens, npk, d);
+    c.bn = w->bn; c.mode = EPI_GATED_BF16; c.act = ACT_SIGMOID; c.layout = LAYOUT_CHANNEL;
+    c.out = side ? Rc : Lc; c.ld_out = chan_stride; c.bias = side ? w->b_right : w->b_left;
+    c.use_rowscale = mask != nullptr; c.rowscale = maskf; c.cm_inner = inner; c.cm_pitch = pitch; c.out_cols = d;
+    AF2_TRY(launch_gemm(c, s));
+  }
+  GemmCall cg = linear_call(xn, d, w->w_ogate, d, (int)tokens, d, d);
+  cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = d; cg.bias = w->b_ogate;
+  AF2_TRY(launch_gemm(cg, s));
+  return AF2_OK;
+}
+
+long long af2_triangle_contract_workspace(int rows, int cols, int d) {
+  return align_up((long long)d * rows * align_up(cols, 4) * 4, 256) + align_up((long long)rows * cols * d * 2, 256) + 1024;
+}
+
+// x [rows, cols, d] (local shard, updated in place) += to_out(LN_c(O) * gate) with
+//   outgoing: O[i][j] = sum_k L[i][k] R[j][k]; L = Lc [c][rows][pitch(K)], piece p of Rg = [c][cols/pieces][pitch(K)]
+//   ingoing : O[i][j] = sum_k R[k][i] L[k][j]; L = Lc [c][K][pitch(cols)],  piece p of Rg = [c][K][pitch(rows/pieces)]
+int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc, long long cs_l, const void* Rg,
+                          long long cs_r, long long piece_stride, int pieces, const void* gate, int rows, int cols,
+                          int K, int d, int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x || !Lc || !Rg || !gate || pieces < 1) return fail(AF2_ERR_BAD_ARG, "triangle_contract: bad argument");
+  if ((!ingoing && cols % pieces) || (ingoing && rows % pieces)) return fail(AF2_ERR_BAD_ARG, "triangle_contract: pieces must divide the gathered axis");
+  const long long T = (long long)rows * cols;
+  const int cp4 = (int)align_up(cols, 4);
+  const long long cs_o = (long long)rows * cp4;
+  Arena ar(workspace, workspace_bytes);
+  float* Oc = ar.take<float>(d * cs_o);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(T * d);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_contract: workspace too small");
+  const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
+  const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
+  for (int p = 0; p < pieces; ++p) {
+    GemmCall c;
+    memset(&c, 0, sizeof(c));
+    c.batch = d; c.K = K; c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.ld_out = cp4; c.out_batch = cs_o;
+    if (!ingoing) {
+      const int pc = cols / pieces;
+      c.A = L; c.lda = align_up(K, 8); c.a_batch = cs_l;
+      c.Bm = R + p * piece_stride; c.ldb = align_up(K, 8); c.b_batch = cs_r;
+      c.mn_major = false; c.M = rows; c.N = pc; c.bn = pick_bn(pc);
+      c.out = Oc + (long long)p * pc;
+    } else {
+      const int pr = rows / pieces;
+      c.A = R + p * piece_stride; c.lda = align_up(pr, 8); c.a_batch = cs_r;
+      c.Bm = L; c.ldb = align_up(cols, 8); c.b_batch = cs_l;
+      c.mn_major = true; c.M = pr; c.N = cols; c.bn = pick_bn(cols);
+      c.out = Oc + (long long)p * pr * cp4;
+    }
+    AF2_TRY(launch_gemm(c, s));
+  }
+  ChanLnParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = cp4; cp.rows = rows; cp.n = cols; cp.d = d; cp.mode = 0;
+  cp.gamma = w->on_gamma; cp.beta = w->on_beta; cp.gate = static_cast<const __nv_bfloat16*>(gate); cp.eps = 1e-5f; cp.y = tn;
+  AF2_TRY(launch_chan_to_token(cp, s));
+  GemmCall co = linear_call(tn, d, w->w_out, d, (int)T, d, d);
+  co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
+  AF2_TRY(launch_gemm(co, s));
+  return AF2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level outer mean
+// ------------------------------------------------------------------------------------------------
+long long af2_outer_project_workspace(long long tokens, int d) {
+  return align_up(tokens * d * 2, 256) + align_up(tokens * 4, 256) + 1024;
+}
+
+// m [S, inner, d] local columns -> LRc bf16 [2d][S*pitch(inner)]: channels [0,d) = left, [d,2d) = right
+int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned char* msa_mask, long long tokens,
+                      int inner, int d, void* LRc, long long chan_stride, void* workspace, long long workspace_bytes,
+                      af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !m || !LRc) return fail(AF2_ERR_BAD_ARG, "outer_project: null argument");
+  if (d % 32) return fail(AF2_ERR_BAD_ARG, "outer_project: dim %d must be a multiple of 32", d);
+  const int pitch = (int)align_up(inner, 8);
+  Arena ar(workspace, workspace_bytes);
+  __nv_bfloat16* mn = ar.take<__nv_bfloat16>(tokens * d);
+  float* maskf = ar.take<float>(tokens);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_project: workspace too small");
+  LnParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.x = m; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = mn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
+  AF2_TRY(launch_layernorm(lp, s));
+  if (msa_mask) {
+    { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(tokens), 256, 0, s>>>(msa_mask, maskf, tokens); }
+    CUDA_OK(cudaGetLastError());
+  }
+  if (pitch != inner) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * chan_stride * 2, s));
+  GemmCall c = linear_call(mn, d, w->w_lr, d, (int)tokens, 2 * d, d);
+  c.mode = EPI_STORE_BF16; c.layout = LAYOUT_CHANNEL; c.out = LRc; c.ld_out = chan_stride; c.bias = w->b_lr;
+  c.use_rowscale = msa_mask != nullptr; c.rowscale = maskf; c.cm_inner = inner; c.cm_pitch = pitch;
+  AF2_TRY(launch_gemm(c, s));
+  return AF2_OK;
+}
+
+long long af2_outer_contract_workspace(int rows, int N, int d) {
+  return align_up((long long)d * rows * align_up(N, 4) * 4, 256) + align_up((long long)rows * N * d * 2, 256) +
+         align_up((long long)rows * N * 4, 256) + 1024;
+}
+
+// x [rows, N, d] (pair rows row0..row0+rows, updated in place) += proj_out( sum_s L[s][i] R[s][j] * scale[i][j] )
+//   L = Lc [c][S][pitch(rows)] (local columns), piece p of Rg = [c][S][pitch(N/pieces)]
+int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, long long cs_l, const void* Rg,
+                       long long cs_r, long long piece_stride, int pieces, const unsigned char* msa_mask_full,
+                       int row0, int rows, int N, int S, int d, float eps, void* workspace, long long workspace_bytes,
+                       af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!w || !x || !Lc || !Rg || pieces < 1 || N % pieces) return fail(AF2_ERR_BAD_ARG, "outer_contract: bad argument");
+  const long long T = (long long)rows * N;
+  const int np4 = (int)align_up(N, 4);
+  const long long cs_o = (long long)rows * np4;
+  Arena ar(workspace, workspace_bytes);
+  float* Oc = ar.take<float>(d * cs_o);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(T * d);
+  float* scale = ar.take<float>(T);
+  if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_contract: workspace too small");
+  if (msa_mask_full) {
+    ProfScope ps(s, KC_MISC, 0.0, 0.0);
+    outer_scale_rows_kernel<<<ew_grid(T), 256, 0, s>>>(msa_mask_full, scale, row0, rows, S, N, eps);
+    CUDA_OK(cudaGetLastError());
+  }
+  const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
+  const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
+  const int pc = N / pieces;
+  for (int p = 0; p < pieces; ++p) {
+    GemmCall g;
+    memset(&g, 0, sizeof(g));
+    g.A = L; g.lda = align_up(rows, 8); g.a_batch = cs_l;
+    g.Bm = R + p * piece_stride; g.ldb = align_up(pc, 8); g.b_batch = cs_r;
+    g.mn_major = true; g.M = rows; g.N = pc; g.K = S; g.batch = d; g.bn = pick_bn(pc);
+    g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)p * pc; g.ld_out = np4; g.out_batch = cs_o;
+    AF2_TRY(launch_gemm(g, s));
+  }
+  ChanLnParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = rows; cp.n = N; cp.d = d; cp.mode = 1;
+  cp.scale = msa_mask_full ? scale : nullptr; cp.scale_const = 1.0f / (float)S; cp.y = tn;
+  AF2_TRY(launch_chan_to_token(cp, s));
+  GemmCall co = linear_call(tn, d, w->w_out, d, (int)T, d, d);
   co.mode = EPI_RESID_F32; co.out = x; co.ld_out = d; co.bias = w->b_out; co.resid = x; co.ld_resid = d;
   AF2_TRY(launch_gemm(co, s));
   return AF2_OK;

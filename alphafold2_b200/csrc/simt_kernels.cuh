@@ -202,6 +202,20 @@ __global__ void outer_scale_kernel(const uint8_t* __restrict__ mask, float* __re
   }
 }
 
+// same for a band of pair rows [row0, row0 + rows) (sharded outer mean): scale[(i - row0) * N + j]
+__global__ void outer_scale_rows_kernel(const uint8_t* __restrict__ mask, float* __restrict__ scale, int row0, int rows,
+                                        int S, int N, float eps) {
+  const long long total = static_cast<long long>(rows) * N;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = idx % N;
+    const int i = row0 + static_cast<int>(idx / N);
+    int cnt = 0;
+    for (int s = 0; s < S; ++s) cnt += (mask[s * N + i] != 0) & (mask[s * N + j] != 0);
+    scale[idx] = 1.0f / (static_cast<float>(S) * (static_cast<float>(cnt) + eps));
+  }
+}
+
 // bool mask -> float 0/1 row scale
 __global__ void mask_to_float_kernel(const uint8_t* __restrict__ mask, float* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;

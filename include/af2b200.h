@@ -102,6 +102,42 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
                    af2_stream_t stream);
 long long af2_outer_mean_workspace(int B, int S, int N, int d);
 
+/* ---------------- stage-level entry points used by the axis-sharded (multi-GPU) schedule ---------------------
+ * The reference has no multi-device path; these split the modules above at the points where the sharded
+ * schedule (alphafold2_b200/parallel.py) must exchange operands over NCCL.  Batch size 1 per call.
+ *   channel-major operand layout: bf16 [channels][chan_stride], token t of a [rows, inner] token grid at
+ *   (t / inner) * align8(inner) + t % inner (pad columns zero). */
+/* pair bias of a band of pair rows: out bf16 [H][rows][align8(n)] = <x[r, j, :], w_edge[h, :]> (w_edge as packed) */
+int af2_pair_bias(const float* x_rows, const float* w_edge, void* bias_out, int rows, int n, int d, int heads,
+                  af2_stream_t stream);
+/* af2_axial_attention with a precomputed bias [B][H][n][align8(n)] (or NULL) instead of raw edges */
+int af2_axial_attention_prebias(const af2_attn_weights* w, float* x, const void* bias_bf16, const unsigned char* mask,
+                                int B, int h, int wdim, int d, int heads, int dim_head, int row_attn, void* workspace,
+                                long long workspace_bytes, af2_stream_t stream);
+/* LN + left/right (masked, gated) -> channel-major Lc, Rc [d][chan_stride]; sigmoid(out_gate) -> gate [tokens, d] */
+int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsigned char* mask, long long tokens,
+                         int inner, int d, void* Lc, void* Rc, long long chan_stride, void* gate, void* workspace,
+                         long long workspace_bytes, af2_stream_t stream);
+long long af2_triangle_project_workspace(long long tokens, int d);
+/* x [rows, cols, d] += to_out(LN_c(O) * gate);  Rg holds `pieces` gathered shards, piece_stride elements apart.
+ *   outgoing: O[i][j] = sum_k L[i][k] R[j][k], L [c][rows][align8(K)], piece p = R rows j of shard p [c][cols/pieces][align8(K)]
+ *   ingoing : O[i][j] = sum_k R[k][i] L[k][j], L [c][K][align8(cols)], piece p = R columns i of shard p [c][K][align8(rows/pieces)] */
+int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc, long long cs_l, const void* Rg,
+                          long long cs_r, long long piece_stride, int pieces, const void* gate, int rows, int cols,
+                          int K, int d, int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream);
+long long af2_triangle_contract_workspace(int rows, int cols, int d);
+/* LN + left|right projections of m [S, inner, d] (masked) -> channel-major LRc [2d][chan_stride] */
+int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned char* msa_mask, long long tokens,
+                      int inner, int d, void* LRc, long long chan_stride, void* workspace, long long workspace_bytes,
+                      af2_stream_t stream);
+long long af2_outer_project_workspace(long long tokens, int d);
+/* pair rows [row0, row0+rows): x [rows, N, d] += proj_out(sum_s L[s][i] R[s][j] * scale_ij); msa_mask_full [S][N] or NULL */
+int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, long long cs_l, const void* Rg,
+                       long long cs_r, long long piece_stride, int pieces, const unsigned char* msa_mask_full,
+                       int row0, int rows, int N, int S, int d, float eps, void* workspace, long long workspace_bytes,
+                       af2_stream_t stream);
+long long af2_outer_contract_workspace(int rows, int N, int d);
+
 /* ---------------- rotary.py:9-20 apply_rotary_pos_emb (dead code at HEAD; standalone op) -------------
  * x, y [b, h, n, dh] fp32; sin, cos [sincos_batch, n, rot] with sincos_batch in {1, b}. */
 int af2_rotary(const float* x, const float* sin_, const float* cos_, float* y, int b, int h, int n, int dh,
