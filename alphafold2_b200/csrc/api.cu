@@ -6,12 +6,14 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../include/af2b200.h"
 #include "attention_tc.cuh"
 #include "gemm_tc.cuh"
+#include "proj_tc.cuh"
 #include "simt_kernels.cuh"
 
 using namespace af2;
@@ -373,6 +375,24 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
 }
 
+#include "proj_launch.inl"
+
+int g_fuse_tail = 0;   // AF2_FUSE_TAIL=1: triangle / outer-mean tails on the fused kernel (a_mode 1 / 2)
+
+// x [T, d] += w_out ( A ) + b_out with A produced from the channel-major fp32 contraction output Oc:
+//   mode 1: A = (LN_c(Oc) * gamma + beta) * gate_cm   (triangle multiply tail)   mode 2: A = Oc * scale (outer mean tail)
+int launch_tail(int a_mode, const float* Oc, long long cs_o, long long T, int d, const float* gamma, const float* beta,
+                const void* gate_cm, const float* scale, float scale_const, const void* w_out, const float* b_out, float* x,
+                cudaStream_t s) {
+  ProjCall pc;
+  memset(&pc, 0, sizeof(pc));
+  pc.a_mode = a_mode; pc.x = Oc; pc.T = T; pc.d = d; pc.src_cs = cs_o; pc.gamma = gamma; pc.beta = beta;
+  pc.gate_cm = gate_cm; pc.gate_cs = T; pc.scale = scale; pc.scale_const = scale_const;
+  pc.w_cat = w_out; pc.b_cat = b_out; pc.w_rows = d; pc.resid = x; pc.ld_resid = d; pc.nseg = 1;
+  pc.seg[0] = ProjOut{1, EK_RESID_F32, d, x, (long long)d};
+  return launch_proj(pc, s);
+}
+
 int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)sm_count() * 8;
@@ -387,7 +407,7 @@ int ew_grid(long long n) {
 extern "C" {
 
 const char* af2_last_error(void) { return g_err; }
-int af2_abi_version(void) { return 1; }
+int af2_abi_version(void) { return 2; }
 
 unsigned long long af2_launch_count(void) { return g_launches; }
 
@@ -416,7 +436,14 @@ long long af2_profile_read(int cls, double* ms, double* flops, double* bytes) {
   return n;
 }
 
+void af2_set_proj_mode(int ctas) {
+  g_fuse_tail = (ctas >= 10) ? 1 : 0;            // 1x: additionally run the triangle / outer-mean tails on the fused kernel
+  ctas %= 10;
+  g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : ctas);
+}
+
 int af2_check_device(void) {
+  if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;
@@ -440,17 +467,27 @@ int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d,
   __nv_bfloat16* xn = ar.take<__nv_bfloat16>(tokens * d);
   __nv_bfloat16* hbuf = ar.take<__nv_bfloat16>(tokens * hidden);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "feed_forward: workspace too small");
-  LnParams lp;
-  memset(&lp, 0, sizeof(lp));
-  lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
-  AF2_TRY(launch_layernorm(lp, s));
   // h = a * gelu(g)
   const int half = w->bn / 2;
   const int n1p = (hidden + half - 1) / half * w->bn;   // packed accumulator columns
-  GemmCall c1 = linear_call(xn, d, w->w1, d, (int)tokens, n1p, d);
-  c1.bn = w->bn; c1.mode = EPI_GATED_BF16; c1.act = ACT_GELU; c1.layout = LAYOUT_TOKEN;
-  c1.out = hbuf; c1.ld_out = hidden; c1.bias = w->b1; c1.out_cols = hidden;
-  AF2_TRY(launch_gemm(c1, s));
+  if (g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d)) {
+    // fused LayerNorm -> Linear -> GEGLU (A-stationary CTA-pair kernel)
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.nseg = 1;
+    pc.seg[0] = ProjOut{n1p / 256, EK_GATED_TOK_GELU, hidden, hbuf, hidden};
+    AF2_TRY(launch_proj(pc, s));
+  } else {
+    LnParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
+    AF2_TRY(launch_layernorm(lp, s));
+    GemmCall c1 = linear_call(xn, d, w->w1, d, (int)tokens, n1p, d);
+    c1.bn = w->bn; c1.mode = EPI_GATED_BF16; c1.act = ACT_GELU; c1.layout = LAYOUT_TOKEN;
+    c1.out = hbuf; c1.ld_out = hidden; c1.bias = w->b1; c1.out_cols = hidden;
+    AF2_TRY(launch_gemm(c1, s));
+  }
   GemmCall c2 = linear_call(hbuf, hidden, w->w2, hidden, (int)tokens, d, hidden);
   c2.mode = EPI_RESID_F32; c2.out = x; c2.ld_out = d; c2.bias = w->b2; c2.resid = x; c2.ld_resid = d;
   AF2_TRY(launch_gemm(c2, s));
@@ -489,6 +526,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   if (pre_bias) bias = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(pre_bias));   // [B][H][n][npad], zero padded
 
   // 1. LayerNorm (+ pair bias from the RAW edges; fused when the edges are x itself)
+  const bool fused_proj = g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && (I % 8) == 0;
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
@@ -498,7 +536,12 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   if (fuse_bias) {
     lp.wb = w->w_edge; lp.bias_out = bias; lp.heads = heads; lp.bias_hs = (long long)n * npad; lp.n_inner = n; lp.pitch = npad;
   }
-  AF2_TRY(launch_layernorm(lp, s));
+  if (!fused_proj) {
+    AF2_TRY(launch_layernorm(lp, s));
+  } else if (fuse_bias) {
+    lp.y = nullptr;                       // pair bias only (raw x . w_edge); the LayerNorm itself is fused into the projection
+    AF2_TRY(launch_layernorm(lp, s));
+  }
   if (has_bias && !fuse_bias && !pre_bias) {
     for (int b = 0; b < B; ++b) {
       LnParams bp;
@@ -510,12 +553,23 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
     }
   }
   // 2. projections
-  GemmCall cq = linear_call(xn, d, w->w_qkv, d, (int)T, (int)(3 * I), d);
-  cq.mode = EPI_STORE_BF16; cq.layout = LAYOUT_TOKEN; cq.out = qkv; cq.ld_out = 3 * I;
-  AF2_TRY(launch_gemm(cq, s));
-  GemmCall cg = linear_call(xn, d, w->w_gate, d, (int)T, (int)I, d);
-  cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = I; cg.bias = w->b_gate;
-  AF2_TRY(launch_gemm(cg, s));
+  if (fused_proj) {
+    // one launch: LayerNorm (+ pair bias) -> [q | k | v] and sigmoid(gating)
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.nseg = 2;
+    pc.seg[0] = ProjOut{(int)((3 * I + 255) / 256), EK_STORE_TOK, (int)(3 * I), qkv, 3 * I};
+    pc.seg[1] = ProjOut{(int)((I + 255) / 256), EK_STORE_TOK_SIG, (int)I, gate, I};
+    AF2_TRY(launch_proj(pc, s));
+  } else {
+    GemmCall cq = linear_call(xn, d, w->w_qkv, d, (int)T, (int)(3 * I), d);
+    cq.mode = EPI_STORE_BF16; cq.layout = LAYOUT_TOKEN; cq.out = qkv; cq.ld_out = 3 * I;
+    AF2_TRY(launch_gemm(cq, s));
+    GemmCall cg = linear_call(xn, d, w->w_gate, d, (int)T, (int)I, d);
+    cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = I; cg.bias = w->b_gate;
+    AF2_TRY(launch_gemm(cg, s));
+  }
   // 3. attention per batch element
   const long long tok_sb = row_attn ? wdim : 1, tok_si = row_attn ? 1 : wdim;
   for (int b = 0; b < B; ++b) {
@@ -561,11 +615,24 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
   float* maskf = ar.take<float>(T);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_multiply: workspace too small");
 
+  const bool fused_front = g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && np8 == N;
+  if (fused_front) {
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = mask; pc.nseg = 3;
+    const int tl = (d + 127) / 128;
+    pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, cs_lr};
+    pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, cs_lr};
+    if (g_fuse_tail) pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_CH_SIG, d, gate, T};   // channel-major gate for the fused tail
+    else pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
+    AF2_TRY(launch_proj(pc, s));
+  }
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
-  AF2_TRY(launch_layernorm(lp, s));
-  if (mask) {
+  if (!fused_front) AF2_TRY(launch_layernorm(lp, s));
+  if (mask && !fused_front) {
     { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(T), 256, 0, s>>>(mask, maskf, T); }
     CUDA_OK(cudaGetLastError());
   }
@@ -576,7 +643,7 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
   // left / right: (proj + b) * mask * sigmoid(gate + b)  -> channel-major [c][b*N + i][k]
   const int half = w->bn / 2;
   const int npk = (d + half - 1) / half * w->bn;
-  for (int side = 0; side < 2; ++side) {
+  for (int side = 0; side < 2 && !fused_front; ++side) {
     GemmCall c = linear_call(xn, d, side ? w->w_right : w->w_left, d, (int)T, npk, d);
     c.bn = w->bn; c.mode = EPI_GATED_BF16; c.act = ACT_SIGMOID; c.layout = LAYOUT_CHANNEL;
     c.out = side ? Rc : Lc; c.ld_out = cs_lr; c.bias = side ? w->b_right : w->b_left;
@@ -585,7 +652,7 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
   }
   GemmCall cg = linear_call(xn, d, w->w_ogate, d, (int)T, d, d);
   cg.mode = EPI_STORE_BF16; cg.act = ACT_SIGMOID; cg.layout = LAYOUT_TOKEN; cg.out = gate; cg.ld_out = d; cg.bias = w->b_ogate;
-  AF2_TRY(launch_gemm(cg, s));
+  if (!fused_front) AF2_TRY(launch_gemm(cg, s));
   // per-channel contraction, batch = channels
   for (int b = 0; b < B; ++b) {
     GemmCall c;
@@ -601,6 +668,8 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
     c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = Oc + (long long)b * N * np4; c.ld_out = np4; c.out_batch = cs_o;
     AF2_TRY(launch_gemm(c, s));
   }
+  if (fused_front && g_fuse_tail)   // LN over channels * out_gate -> to_out -> + residual in one launch
+    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->b_out, x, s);
   // LN over channels * out_gate -> token-major bf16
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
@@ -640,22 +709,32 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   float* scale = ar.take<float>(Tx);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_mean: workspace too small");
 
+  const bool fused_front = g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && np8 == N;
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = m; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = mn; lp.T = Tm; lp.d = d; lp.eps = 1e-5f;
-  AF2_TRY(launch_layernorm(lp, s));
+  if (!fused_front) AF2_TRY(launch_layernorm(lp, s));
   if (msa_mask) {
-    { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm); }
+    if (!fused_front) { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm); }
     CUDA_OK(cudaGetLastError());
     { ProfScope ps(s, KC_MISC, 0.0, 0.0); outer_scale_kernel<<<ew_grid(Tx), 256, 0, s>>>(msa_mask, scale, B, S, N, eps); }
     CUDA_OK(cudaGetLastError());
   }
   if (np8 != N) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * cs_lr * 2, s));
   // [left | right] = (LN(m) W^T + b) * mask  -> channel-major [c][b*S + s][i]
-  GemmCall c = linear_call(mn, d, w->w_lr, d, (int)Tm, 2 * d, d);
-  c.mode = EPI_STORE_BF16; c.layout = LAYOUT_CHANNEL; c.out = LRc; c.ld_out = cs_lr; c.bias = w->b_lr;
-  c.use_rowscale = msa_mask != nullptr; c.rowscale = maskf; c.cm_inner = N; c.cm_pitch = np8;
-  AF2_TRY(launch_gemm(c, s));
+  if (fused_front) {
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = m; pc.T = Tm; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = msa_mask; pc.nseg = 1;
+    pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, cs_lr};
+    AF2_TRY(launch_proj(pc, s));
+  } else {
+    GemmCall c = linear_call(mn, d, w->w_lr, d, (int)Tm, 2 * d, d);
+    c.mode = EPI_STORE_BF16; c.layout = LAYOUT_CHANNEL; c.out = LRc; c.ld_out = cs_lr; c.bias = w->b_lr;
+    c.use_rowscale = msa_mask != nullptr; c.rowscale = maskf; c.cm_inner = N; c.cm_pitch = np8;
+    AF2_TRY(launch_gemm(c, s));
+  }
   // O_c[i][j] = sum_s L_c[s][i] R_c[s][j]  (MN-major operands, K = S)
   for (int b = 0; b < B; ++b) {
     GemmCall g;
@@ -666,6 +745,8 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
     g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)b * N * np4; g.ld_out = np4; g.out_batch = cs_o;
     AF2_TRY(launch_gemm(g, s));
   }
+  if (fused_front && g_fuse_tail)
+    return launch_tail(2, Oc, cs_o, Tx, d, nullptr, nullptr, nullptr, msa_mask ? scale : nullptr, 1.0f / (float)S, w->w_out, w->b_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = B * N; cp.n = N; cp.d = d; cp.mode = 1;
@@ -725,6 +806,18 @@ int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsi
   __nv_bfloat16* xn = ar.take<__nv_bfloat16>(tokens * d);
   float* maskf = ar.take<float>(tokens);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_project: workspace too small");
+  if (g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && pitch == inner) {
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = mask; pc.nseg = 3;
+    const int tl = (d + 127) / 128;
+    pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, chan_stride};
+    pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, chan_stride};
+    if (g_fuse_tail) pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_CH_SIG, d, gate, tokens};   // channel-major, consumed by af2_triangle_contract
+    else pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
+    return launch_proj(pc, s);
+  }
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
@@ -793,6 +886,8 @@ int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc,
     }
     AF2_TRY(launch_gemm(c, s));
   }
+  if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && cols % 8 == 0)   // same predicate as af2_triangle_project
+    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->b_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = cp4; cp.rows = rows; cp.n = cols; cp.d = d; cp.mode = 0;
@@ -823,6 +918,14 @@ int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned
   __nv_bfloat16* mn = ar.take<__nv_bfloat16>(tokens * d);
   float* maskf = ar.take<float>(tokens);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_project: workspace too small");
+  if (g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && pitch == inner) {
+    ProjCall pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.a_mode = 0; pc.x = m; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = msa_mask; pc.nseg = 1;
+    pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, chan_stride};
+    return launch_proj(pc, s);
+  }
   LnParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.x = m; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = mn; lp.T = tokens; lp.d = d; lp.eps = 1e-5f;
@@ -877,6 +980,8 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
     g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)p * pc; g.ld_out = np4; g.out_batch = cs_o;
     AF2_TRY(launch_gemm(g, s));
   }
+  if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && N % 4 == 0)
+    return launch_tail(2, Oc, cs_o, T, d, nullptr, nullptr, nullptr, msa_mask_full ? scale : nullptr, 1.0f / (float)S, w->w_out, w->b_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = rows; cp.n = N; cp.d = d; cp.mode = 1;

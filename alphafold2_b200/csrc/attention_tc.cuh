@@ -69,8 +69,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t SWZ = (DH == 64) ? SWZ_128 : SWZ_64;
   constexpr uint32_t ROWB = DH * 2;                 // bytes per Q/K/V row
   constexpr uint32_t SBO = 8 * ROWB;                // 8-row swizzle atom
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte aligned by declaration (128B-swizzle atoms); keeping the array symbol (no integer round-up of the pointer)
+  // lets the compiler prove the shared address space and emit LDS/STS instead of generic LD/ST
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* q_full = bars + 0;     // Q tile landed
   uint64_t* g_full = bars + 1;     // [2] gate tile landed (slot it & 1)

@@ -1,0 +1,756 @@
+// Fused  [A-producer] -> multi-segment projection GEMM  for K = d <= 256 on tcgen05, CTA-pair (cta_group::2) MMA.
+//
+//   out_seg = epilogue_seg( A[T, d] * Wcat[tiles of 256 rows, d]^T + bcat )        A produced IN the kernel:
+//     mode 0: A = (x - mean(x)) * rstd(x)               x fp32 token-major [T, d].  The LayerNorm affine is folded into
+//             the packed operands on the host (W' = W diag(gamma), b' = W beta + b), so this IS LayerNorm -> Linear
+//             (alphafold2.py:82-85, 210-217 + 114-118, 269-276 + 297-311, 330-340); optional pair-bias side output
+//             bias[h][pos(t)] = <x_raw[t], w_edge[h]>  (alphafold2.py:214-217, 245-247)
+//     mode 1: A = (LayerNorm_c(O[c][t]) * gamma + beta) * gate[c][t]   O fp32 channel-major, gate bf16 channel-major
+//             (triangle-multiply tail, alphafold2.py:315-316)
+//     mode 2: A = O[c][t] * scale[t]                                  (outer-mean tail, alphafold2.py:345-349)
+//
+// Why this shape: the K = 256 projections of the Evoformer are L2->SM bandwidth bound when tiled 128 x 256 with
+// both operands streamed (192 KB of operand per 16.8 MFLOP; the L2 caps near 6300 B/clk chip-wide).  Here
+//   * the A tile (128 rows x d, bf16, 64 KB) is produced once per work item by SIMT warps straight from the fp32
+//     residual stream (no LayerNorm kernel, no bf16 round trip through HBM) and stays resident (double buffered)
+//     while ALL column tiles of the item stream past it;
+//   * two CTAs of a cluster form a pair: one tcgen05.mma.cta_group::2 covers M = 256 rows (128 per CTA) x N = 256,
+//     each CTA stages only its half of the weight tile (TMA, 16 KB per k-block), halving weight traffic per FLOP;
+//   * one launch serves several outputs with different epilogue programs (q|k|v + gate; left + right + out-gate ...)
+//     so the normalised activations are never re-read.
+// The kernel is specialised at compile time on (pair / single CTA, producer mode, set of epilogue kinds) so each
+// instantiation carries only the code it runs (the all-in-one version was instruction-cache bound).
+// Warp roles per CTA (512 threads): 0 weight-tile TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator |
+// 3 residual prefetch into the staging buffers (EK_RESID_F32 only) | 4..11 epilogue, two groups of four warps, each
+// group with its own 16 KB staging buffer (TMEM -> regs -> swizzled smem -> TMA store) | 12..15 A producers.
+// Accumulators are double buffered in TMEM (2 x 256 columns per CTA).
+#pragma once
+#include "gemm_tc.cuh"
+#include "simt_kernels.cuh"
+
+namespace af2 {
+
+constexpr int PROJ_THREADS = 512;
+constexpr int PROJ_MAX_SEG = 4;
+constexpr int PROJ_A_BUF = 65536;          // 128 rows x 256 K bf16 (4 k-blocks of 16 KB)
+
+__host__ __device__ constexpr int KBIT(int ek) { return 1 << ek; }
+// epilogue-kind sets of the instantiations
+constexpr int PK_ATTN = KBIT(EK_STORE_TOK) | KBIT(EK_STORE_TOK_SIG);      // [q|k|v] + sigmoid(gating)
+constexpr int PK_TRI = KBIT(EK_GATED_CH_SIG) | KBIT(EK_STORE_TOK_SIG);    // left, right (gated, masked, channel-major) + out gate
+constexpr int PK_TRI_CH = KBIT(EK_GATED_CH_SIG) | KBIT(EK_STORE_CH_SIG);  // ... with a channel-major out gate (fused tail)
+constexpr int PK_FF = KBIT(EK_GATED_TOK_GELU);                            // GEGLU
+constexpr int PK_OUTER = KBIT(EK_STORE_CH);                               // left | right (masked, channel-major)
+constexpr int PK_TAIL = KBIT(EK_RESID_F32);                               // output projection + residual
+
+struct ProjSeg {
+  int tile0, ntiles;     // accumulator-column tiles (256 columns each) [tile0, tile0 + ntiles)
+  int kind;              // EpiKind
+  int out_cols;          // valid output columns of the segment
+  int map;               // output tensor map index (0..2)
+  int pad;
+};
+
+struct ProjParams {
+  // ---- A producer ----
+  const float* x;                // mode 0: [T, d] fp32;  mode 1/2: channel-major fp32, element (c, t) at c*src_cs + t
+  long long T;
+  int d;
+  float inv_d;
+  long long src_cs;              // channel stride (modes 1/2)
+  const float* gamma;            // modes 1 only (mode 0: folded into the weights)
+  const float* beta;
+  float eps;
+  const __nv_bfloat16* gate_cm;  // mode 1: bf16 channel-major gate, element (c, t) at c*gate_cs + t
+  long long gate_cs;
+  const float* scale;            // mode 2: [T] or nullptr -> scale_const
+  float scale_const;
+  // pair-bias side output (mode 0, PK_ATTN)
+  const float* wb;               // [H, d] fp32 or nullptr
+  __nv_bfloat16* bias_out;
+  int heads;
+  long long bias_hs;
+  int n_inner, pitch;
+  // ---- GEMM / epilogue ----
+  const float* bcat;             // [n_tiles_total * 256] fp32 bias in accumulator-column order (zeros where none)
+  const unsigned char* rowmask;  // [T] bool row scale or nullptr (kinds with rowscale)
+  int nseg;
+  ProjSeg seg[PROJ_MAX_SEG];
+  int n_tiles_total;
+  int nsplit;                    // column chunks per row unit
+  int m_tiles;                   // ceil(T / 128)
+};
+
+template <int CTAS>
+struct ProjSmem {
+  static constexpr int STAGES = CTAS == 2 ? 3 : 2;                    // the MMA never waited on weight stages with 4
+  static constexpr int B_ROWS = 256 / CTAS;
+  static constexpr int B_STAGE = B_ROWS * GEMM_BK * 2;               // 16 KB (pair) / 32 KB
+  static constexpr int EPI_BUFS = 2;                                  // one per epilogue warp group
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = 2 * PROJ_A_BUF;
+  static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE;
+  static constexpr int BIAS_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;  // fp32 bias rows of every column tile (pair only)
+  static constexpr int BIAS_TILES = CTAS == 2 ? 12 : 0;
+  static constexpr int BAR_OFF = BIAS_OFF + BIAS_TILES * 1024;
+  static constexpr int TOTAL = BAR_OFF + 512;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
+//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
+//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
+//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`.  Values are finished in
+//    registers BEFORE the buffer is reclaimed, so the previous TMA store's smem read overlaps the math.
+// ---------------------------------------------------------------------------------------------------
+// bias rows live in shared memory (broadcast LDS) when they fit: global loads here missed L1 (the producers stream the
+// activations through it) and their L2 round trips were the epilogue's critical path
+template <bool SMEM>
+__device__ __forceinline__ float4 proj_bias_ld4(const float* bias, int j) {
+  float4 t4;
+  if constexpr (SMEM) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                 : "r"(smem_u32(bias) + j * 16));
+  } else {
+    t4 = __ldg(reinterpret_cast<const float4*>(bias) + j);
+  }
+  return t4;
+}
+template <bool SMEM>
+__device__ __forceinline__ void proj_bias_store32(uint32_t taddr, const float* bias) {
+  uint32_t b[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t4 = proj_bias_ld4<SMEM>(bias, j);
+    b[4 * j] = __float_as_uint(t4.x); b[4 * j + 1] = __float_as_uint(t4.y);
+    b[4 * j + 2] = __float_as_uint(t4.z); b[4 * j + 3] = __float_as_uint(t4.w);
+  }
+  tmem_st32(taddr, b);
+}
+template <bool SMEM>
+__device__ __forceinline__ void proj_bias_store16(uint32_t taddr, const float* bias) {
+  uint32_t b[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t4 = proj_bias_ld4<SMEM>(bias, j);
+    b[4 * j] = __float_as_uint(t4.x); b[4 * j + 1] = __float_as_uint(t4.y);
+    b[4 * j + 2] = __float_as_uint(t4.z); b[4 * j + 3] = __float_as_uint(t4.w);
+  }
+  tmem_st16(taddr, b);
+}
+
+// Finish 32 output columns held in registers (u [, g]): activation / gate, row scale, pack to bf16x2.
+template <int EK>
+__device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t* g, float rs, uint32_t (&pk)[16]) {
+  constexpr int mode = EpiTraits<EK>::mode, act = EpiTraits<EK>::act;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a;
+    if constexpr (mode == EPI_GATED_BF16) {
+      const float gg = __uint_as_float(g[j]);
+      if constexpr (act == ACT_GELU) a = gelu_fast(gg);
+      else a = sigmoidf_fast(gg);
+      a *= __uint_as_float(u[j]);
+    } else {
+      a = __uint_as_float(u[j]);
+      if constexpr (act == ACT_SIGMOID) a = sigmoidf_fast(a);
+    }
+    if constexpr (EpiTraits<EK>::rowscale) a *= rs;
+    v[j] = a;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+}
+
+// 32 packed output columns (tile-local output columns co .. co+31 of the 64-column chunk) -> swizzled staging buffer
+template <int LAYOUT>
+__device__ __forceinline__ void proj_stage32(uint8_t* eb, int row_in_tile, int half, const uint32_t (&pk)[16]) {
+  if constexpr (LAYOUT == LAYOUT_TOKEN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(eb + swz128_off(row_in_tile, half * 4 + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  } else {
+    // staging holds [64 channels][128 tokens] as two 64-token boxes of 64 rows x 128 B
+    uint8_t* bx = eb + (row_in_tile >> 6) * 8192;
+    const uint32_t tl = row_in_tile & 63;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t c0 = half * 32 + 2 * j, c1 = c0 + 1;
+      *reinterpret_cast<uint16_t*>(bx + c0 * 128 + ((((tl >> 3) ^ (c0 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] & 0xffffu);
+      *reinterpret_cast<uint16_t*>(bx + c1 * 128 + ((((tl >> 3) ^ (c1 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] >> 16);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
+//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
+//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
+//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`.  Values are finished in
+//    registers BEFORE the buffer is reclaimed, so the previous TMA store's smem read overlaps the math.
+// ---------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
+//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
+//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
+//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`; a chunk is produced 16 columns
+//    at a time straight into the swizzled staging buffer (low register pressure), then stored with one TMA store.
+// ---------------------------------------------------------------------------------------------------
+template <int EK, bool SB>
+__device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* efull_bar, uint64_t* eempty_bar, uint32_t& ec,
+                                                   uint32_t& gc, int grp, bool leader_thread, uint32_t t_acc,
+                                                   const CUtensorMap* tmc, const float* bias_next, float rs, int row_in_tile,
+                                                   int m0, int col0, int ncols) {
+  constexpr int mode = EpiTraits<EK>::mode, layout = EpiTraits<EK>::layout;
+  constexpr bool out_f32 = (mode == EPI_RESID_F32) || (mode == EPI_STORE_F32);
+  constexpr bool gated = (mode == EPI_GATED_BF16);
+  constexpr int CW = out_f32 ? 32 : 64;
+  constexpr int W = gated ? 128 : 256;
+  const int nchunks = (ncols + CW - 1) / CW;
+  uint8_t* eb = epi_base + grp * EPI_BUF_BYTES;
+  for (int cc = 0; cc < nchunks; ++cc, ++ec) {
+    if ((ec & 1) != static_cast<uint32_t>(grp)) continue;
+    if constexpr (out_f32) {
+      uint32_t u[32];
+      tmem_ld32(t_acc + cc * 32, u);
+      tmem_ld_wait();
+      if (bias_next) proj_bias_store32<SB>(t_acc + cc * 32, bias_next + cc * 32);
+      // reclaim the buffer: the group's previous store must have read it; the residual tile is then prefetched into it
+      if (leader_thread) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&eempty_bar[grp]);
+      }
+      mbar_wait(&efull_bar[grp], gc & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4* sp = reinterpret_cast<float4*>(eb + swz128_off(row_in_tile, j));
+        float4 o = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
+                               __uint_as_float(u[4 * j + 3]));
+        if constexpr (mode == EPI_RESID_F32) {
+          const float4 r4 = *sp;
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        *sp = o;
+      }
+    } else {
+      // All TMEM loads of the chunk are issued up front (one round trip of latency per chunk instead of four), the
+      // buffer reclaim overlaps them, and the bias of the stage's next user goes back with asynchronous tcgen05.st.
+      if constexpr (gated) {
+        uint32_t u0[32], g0[32];
+        tmem_ld32(t_acc + cc * 64, u0);
+        tmem_ld32(t_acc + 128 + cc * 64, g0);
+        if (leader_thread) tma_store_wait_read<0>();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        tmem_ld_wait();
+        uint32_t u1[32], g1[32];
+        tmem_ld32(t_acc + cc * 64 + 32, u1);            // second half in flight while the first is finished
+        tmem_ld32(t_acc + 128 + cc * 64 + 32, g1);
+        {
+          uint32_t pk[16];
+          proj_finish32<EK>(u0, g0, rs, pk);
+          proj_stage32<layout>(eb, row_in_tile, 0, pk);
+        }
+        tmem_ld_wait();
+        {
+          uint32_t pk[16];
+          proj_finish32<EK>(u1, g1, rs, pk);
+          proj_stage32<layout>(eb, row_in_tile, 1, pk);
+        }
+        if (bias_next) {
+          proj_bias_store32<SB>(t_acc + cc * 64, bias_next + cc * 64);
+          proj_bias_store32<SB>(t_acc + cc * 64 + 32, bias_next + cc * 64 + 32);
+          proj_bias_store32<SB>(t_acc + 128 + cc * 64, bias_next + 128 + cc * 64);
+          proj_bias_store32<SB>(t_acc + 128 + cc * 64 + 32, bias_next + 128 + cc * 64 + 32);
+        }
+      } else {
+        uint32_t u0[32], u1[32];
+        tmem_ld32(t_acc + cc * 64, u0);
+        tmem_ld32(t_acc + cc * 64 + 32, u1);
+        if (leader_thread) tma_store_wait_read<0>();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        tmem_ld_wait();
+        if (bias_next) {
+          proj_bias_store32<SB>(t_acc + cc * 64, bias_next + cc * 64);
+          proj_bias_store32<SB>(t_acc + cc * 64 + 32, bias_next + cc * 64 + 32);
+        }
+        {
+          uint32_t pk[16];
+          proj_finish32<EK>(u0, nullptr, rs, pk);
+          proj_stage32<layout>(eb, row_in_tile, 0, pk);
+        }
+        {
+          uint32_t pk[16];
+          proj_finish32<EK>(u1, nullptr, rs, pk);
+          proj_stage32<layout>(eb, row_in_tile, 1, pk);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (leader_thread) {
+      if constexpr (layout == LAYOUT_TOKEN) {
+        tma_store_3d(tmc, eb, col0 + cc * CW, m0, 0);
+      } else {
+        tma_store_3d(tmc, eb, m0, col0 + cc * 64, 0);
+        tma_store_3d(tmc, eb + 8192, m0 + 64, col0 + cc * 64, 0);
+      }
+      tma_store_commit();
+    }
+    ++gc;
+  }
+  // output columns clipped away (ragged last tile of a segment) are read by nobody: group 0 re-initialises them
+  if (bias_next && grp == 0) {
+    for (int c = nchunks * CW; c < W; c += 32) {
+      proj_bias_store32<SB>(t_acc + c, bias_next + c);
+      if constexpr (gated) proj_bias_store32<SB>(t_acc + 128 + c, bias_next + 128 + c);
+    }
+  }
+}
+
+__device__ __forceinline__ int proj_tile_width(int kind) {
+  return (kind == EK_GATED_TOK_GELU || kind == EK_GATED_CH_SIG) ? 128 : 256;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mode-0 producer helpers.  Eight lanes share a row (4 rows per warp instruction): lane l of a row group owns float4
+// chunks l, l + 8, ... of the row, so a load instruction reads 128 contiguous bytes per row, the two row reductions
+// need 3 shuffle levels instead of 5, and ~50 warp instructions produce one normalised row (one-warp-per-row: ~270).
+// ---------------------------------------------------------------------------------------------------
+struct RowQuad { float4 v[8]; };     // this lane's 32 values of its row (d <= 256)
+
+// streaming 16-byte load that does not allocate in L1 (the activations are read once; L1 is left to the small hot data)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void proj_load_quad(RowQuad& b, const float* x, long long row, long long T, int d, int nj, int sub) {
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    b.v[j] = (row < T && j < nj) ? ldg_stream(xr + j * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abuf, int r, bool live, float inv_d, float eps, int nj,
+                                                  int sub) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += (b.v[j].x + b.v[j].y) + (b.v[j].z + b.v[j].w);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float mean = s * inv_d;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < nj) {
+      const float a = b.v[j].x - mean, bb = b.v[j].y - mean, cc = b.v[j].z - mean, dd = b.v[j].w - mean;
+      sq += a * a + bb * bb + cc * cc + dd * dd;
+    }
+  }
+  sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+  sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+  sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+  const float rs = live ? rsqrtf(sq * inv_d + eps) : 0.f;      // dead rows (beyond T) become zeros
+  const float sh = -mean * rs;
+  // float4 chunk idx = j*8 + sub covers columns 4*idx..: k-block idx/16 = j/2, 16-byte chunk (idx%16)/2, half idx&1
+  uint8_t* rowp = abuf + r * 128;
+  const uint32_t sw = static_cast<uint32_t>(r & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < nj) {
+      const uint32_t chunk = static_cast<uint32_t>(((j & 1) * 8 + sub) >> 1);
+      const uint2 o = make_uint2(pack_bf16x2(fmaf(b.v[j].x, rs, sh), fmaf(b.v[j].y, rs, sh)),
+                                 pack_bf16x2(fmaf(b.v[j].z, rs, sh), fmaf(b.v[j].w, rs, sh)));
+      *reinterpret_cast<uint2*>(rowp + (j >> 1) * 16384 + ((chunk ^ sw) << 4) + (sub & 1) * 8) = o;
+    }
+  }
+}
+
+template <int CTAS, int AMODE, int KINDS>
+__global__ void __launch_bounds__(PROJ_THREADS, 1)
+proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
+               const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ProjParams p) {
+  using L = ProjSmem<CTAS>;
+  constexpr int STAGES = L::STAGES;
+  constexpr bool HAS_RESID = (KINDS & KBIT(EK_RESID_F32)) != 0;
+  constexpr bool HAS_BIAS = false;   // pair-bias side output of the producer: correct but slow (4 warps); the host uses the
+                                     // bias-only LayerNorm launch instead
+  // 1024-byte aligned by declaration (128B-swizzle atoms); keeping the array symbol (no integer round-up of the pointer)
+  // lets the compiler prove the shared address space and emit LDS/STS instead of generic LD/ST
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);   // [STAGES] weight stage landed (leader's)
+  uint64_t* empty_bar = full_bar + STAGES;                                // [STAGES] weight stage consumed
+  uint64_t* tfull_bar = empty_bar + STAGES;                               // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;                                   // [2] accumulator drained (leader's)
+  uint64_t* efull_bar = tempty_bar + 2;                                   // [2] residual tile landed in group buffer
+  uint64_t* eempty_bar = efull_bar + 2;                                   // [2] group buffer reclaimed
+  uint64_t* afull_bar = eempty_bar + 2;                                   // [2] A buffer produced (leader's)
+  uint64_t* aempty_bar = afull_bar + 2;                                   // [2] A buffer consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = rank == 0;
+  const int cluster_id = blockIdx.x / CTAS;
+  const int nclusters = gridDim.x / CTAS;
+  constexpr uint32_t TMEM_COLS = 512;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8 * CTAS);
+      mbar_init(&afull_bar[s], 4 * CTAS);
+      mbar_init(&aempty_bar[s], 1);
+      mbar_init(&efull_bar[s], 1);
+      mbar_init(&eempty_bar[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    if constexpr (CTAS == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  // stage the bias rows of every column tile in shared memory (all threads; visible after the sync below)
+  constexpr bool sbias = L::BIAS_TILES > 0;       // host guarantees n_tiles_total <= BIAS_TILES for the pair kernel
+  if constexpr (sbias) {
+    float4* dst = reinterpret_cast<float4*>(smem + L::BIAS_OFF);
+    const float4* src = reinterpret_cast<const float4*>(p.bcat);
+    for (int i = threadIdx.x; i < p.n_tiles_total * 64; i += PROJ_THREADS) dst[i] = __ldg(src + i);
+  }
+  const float* bias_base = sbias ? reinterpret_cast<const float*>(smem + L::BIAS_OFF) : p.bcat;
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- work decomposition: item = (row unit of 128*CTAS rows, column chunk) ----
+  const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
+  const int total_items = m_units * p.nsplit;
+  const int tiles_per_chunk = (p.n_tiles_total + p.nsplit - 1) / p.nsplit;
+  const int my_items = (total_items > cluster_id) ? (total_items - 1 - cluster_id) / nclusters + 1 : 0;
+  const int nkb = p.d / GEMM_BK;
+  auto item_unit = [&](int it) { return (cluster_id + it * nclusters) / p.nsplit; };
+  auto item_chunk = [&](int it) { return (cluster_id + it * nclusters) % p.nsplit; };
+  auto chunk_t0 = [&](int ch) { return ch * tiles_per_chunk; };
+  auto chunk_t1 = [&](int ch) { return min((ch + 1) * tiles_per_chunk, p.n_tiles_total); };
+  auto seg_of = [&](int nt) {
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < PROJ_MAX_SEG; ++i)
+      if (i < p.nseg && nt >= p.seg[i].tile0) s = i;
+    return s;
+  };
+
+  if (warp == 0) {
+    // ================================ weight-tile TMA producer ================================
+    if (lane == 0) {
+      uint32_t full_remote[STAGES];
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) full_remote[s] = (CTAS == 2) ? mapa_u32(smem_u32(&full_bar[s]), 0) : 0u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int ch = item_chunk(it);
+        for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sb = smem + L::B_OFF + stage * L::B_STAGE;
+            if constexpr (CTAS == 2) {
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::B_STAGE);
+              tma_load_2d_pair(sb, &tmB, full_remote[stage], kb * GEMM_BK, nt * 256 + static_cast<int>(rank) * L::B_ROWS);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], L::B_STAGE);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * 256);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA) =================================
+    if (is_leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CTAS, 256, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tcnt = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int ab = it & 1;
+        const int ch = item_chunk(it);
+        mbar_wait(&afull_bar[ab], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sa0 = smem_u32(smem + L::A_OFF + ab * PROJ_A_BUF);
+        const int t1 = chunk_t1(ch);
+        for (int nt = chunk_t0(ch); nt < t1; ++nt, ++tcnt) {
+          const int acc = tcnt & 1;
+          mbar_wait(&tempty_bar[acc], (tcnt >> 1) & 1);     // completion #k: bias preloaded (k = 0) / stage drained + preloaded
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = sa0 + kb * 16384;
+              const uint32_t sb = smem_u32(smem + L::B_OFF + stage * L::B_STAGE);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) {
+                const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, 1024, SWZ_128);
+                const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, 1024, SWZ_128);
+                if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 1u);   // accumulator starts at the bias
+                else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+              }
+              if constexpr (CTAS == 2) {
+                umma_commit_pair(&empty_bar[stage], 3);
+                if (kb == nkb - 1) {
+                  umma_commit_pair(&tfull_bar[acc], 3);
+                  if (nt == t1 - 1) umma_commit_pair(&aempty_bar[ab], 3);
+                }
+              } else {
+                umma_commit(&empty_bar[stage]);
+                if (kb == nkb - 1) {
+                  umma_commit(&tfull_bar[acc]);
+                  if (nt == t1 - 1) umma_commit(&aempty_bar[ab]);
+                }
+              }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== residual prefetch into the epilogue groups' staging buffers ==================
+    if constexpr (HAS_RESID) {
+      if (lane == 0) {
+        uint32_t ec = 0, gcnt[2] = {0u, 0u};
+        for (int it = 0; it < my_items; ++it) {
+          const int unit = item_unit(it), ch = item_chunk(it);
+          const int m0 = (unit * CTAS + static_cast<int>(rank)) * 128;
+          for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt) {
+            const ProjSeg& sg = p.seg[seg_of(nt)];
+            const int col0 = (nt - sg.tile0) * 256;
+            const int ncols = min(256, sg.out_cols - col0);
+            const int nchunks = ncols > 0 ? (ncols + 31) / 32 : 0;
+            for (int cc = 0; cc < nchunks; ++cc, ++ec) {
+              const int g = ec & 1;
+              const uint32_t k = gcnt[g]++;
+              mbar_wait(&eempty_bar[g], k & 1);                    // group g reclaimed its buffer for its k-th chunk
+              mbar_arrive_expect_tx(&efull_bar[g], EPI_BUF_BYTES);
+              tma_load_3d(smem + L::EPI_OFF + g * EPI_BUF_BYTES, &tmR, &efull_bar[g], col0 + cc * 32, m0, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const bool leader_thread = (threadIdx.x == 128 + grp * 128);
+    uint32_t tempty_remote[2];
+    tempty_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+    tempty_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
+    uint8_t* epi_base = smem + L::EPI_OFF;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    // n-tile index of the k-th tile of this cluster's sequence (or -1): items are walked in order, each with its chunk
+    auto tile_at = [&](int it, int nt, int steps, int& nt_out) {
+      while (it < my_items) {
+        const int t1 = chunk_t1(item_chunk(it));
+        if (nt + steps < t1) { nt_out = nt + steps; return true; }
+        steps -= (t1 - nt);
+        ++it;
+        if (it < my_items) nt = chunk_t0(item_chunk(it));
+      }
+      return false;
+    };
+    // prime both accumulator stages with the bias of the first two tiles (group g preloads column blocks g, g+2, ...)
+    if (my_items > 0) {
+      for (int a = 0; a < 2; ++a) {
+        int ntp;
+        if (tile_at(0, chunk_t0(item_chunk(0)), a, ntp)) {
+          const float* bp = bias_base + static_cast<long long>(ntp) * 256;
+          for (int c = grp * 32; c < 256; c += 64) proj_bias_store32<sbias>(tmem_base + a * 256 + lane_sel + c, bp + c);
+        }
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      for (int a = 0; a < 2; ++a) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_remote[a]);
+        else mbar_arrive(&tempty_bar[a]);
+      }
+    }
+    uint32_t ec = 0, gc = 0, tcnt = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int unit = item_unit(it), ch = item_chunk(it);
+      const int m0 = (unit * CTAS + static_cast<int>(rank)) * 128;
+      const long long row = static_cast<long long>(m0) + row_in_tile;
+      float rs = 1.0f;
+      if (p.rowmask && row < p.T) rs = p.rowmask[row] ? 1.0f : 0.0f;
+      for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt, ++tcnt) {
+        const ProjSeg& sg = p.seg[seg_of(nt)];
+        const int acc = tcnt & 1;
+        const int W = proj_tile_width(sg.kind);
+        const int col0 = (nt - sg.tile0) * W;
+        const int ncols = min(W, sg.out_cols - col0);
+        int nt2;
+        const float* bias_next = tile_at(it, nt, 2, nt2) ? bias_base + static_cast<long long>(nt2) * 256 : nullptr;
+        const CUtensorMap* tmc = sg.map == 0 ? &tmC0 : (sg.map == 1 ? &tmC1 : &tmC2);
+        mbar_wait(&tfull_bar[acc], (tcnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + acc * 256 + lane_sel;
+#define AF2_PROJ_CASE(EKV)                                                                                               \
+  if constexpr ((KINDS & KBIT(EKV)) != 0) {                                                                              \
+    if (sg.kind == EKV)                                                                                                  \
+      proj_epilogue_tile<EKV, sbias>(epi_base, efull_bar, eempty_bar, ec, gc, grp, leader_thread, t_acc, tmc,            \
+                                     bias_next, rs, row_in_tile, m0, col0, ncols > 0 ? ncols : 0);                       \
+  }
+        AF2_PROJ_CASE(EK_STORE_TOK)
+        AF2_PROJ_CASE(EK_STORE_TOK_SIG)
+        AF2_PROJ_CASE(EK_STORE_CH)
+        AF2_PROJ_CASE(EK_STORE_CH_SIG)
+        AF2_PROJ_CASE(EK_GATED_TOK_GELU)
+        AF2_PROJ_CASE(EK_GATED_CH_SIG)
+        AF2_PROJ_CASE(EK_RESID_F32)
+#undef AF2_PROJ_CASE
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_remote[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      }
+    }
+    if (leader_thread) tma_store_wait_read<0>();
+  } else if (warp >= 12) {
+    // ================================ A producers ====================================
+    const int pw = warp - 12;
+    uint32_t afull_remote[2];
+    afull_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[0]), 0) : 0u;
+    afull_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[1]), 0) : 0u;
+    const int nchunk = p.d >> 2;                 // float4 chunks per row (<= 64)
+    const int sub = lane & 7;                    // lane within its row group
+    const int rg = lane >> 3;                    // row group 0..3 of the warp instruction
+    const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32 <= 8)
+    RowQuad qa, qb;
+    if constexpr (AMODE == 0) {
+      if (my_items > 0)
+        proj_load_quad(qa, p.x, static_cast<long long>(item_unit(0) * CTAS + static_cast<int>(rank)) * 128 + pw * 32 + rg, p.T, p.d, nj, sub);
+    }
+    for (int it = 0; it < my_items; ++it) {
+      const int unit = item_unit(it), ch = item_chunk(it);
+      const long long m0 = static_cast<long long>(unit * CTAS + static_cast<int>(rank)) * 128;
+      const int ab = it & 1;
+      uint8_t* abuf = smem + L::A_OFF + ab * PROJ_A_BUF;
+      mbar_wait(&aempty_bar[ab], ((it >> 1) & 1) ^ 1);
+      if constexpr (AMODE == 0) {
+        // ---- token-major LayerNorm core: 4 rows per warp instruction, 8 steps per item, next step's loads in flight ----
+        (void)ch;
+        const int r0 = pw * 32 + rg;             // this lane's row inside the tile at step 0 (step s: + 4 s)
+        const long long rbase = m0 + r0;
+        long long next_base = -1;                // first step of the next item (cross-item prefetch)
+        if (it + 1 < my_items) {
+          next_base = static_cast<long long>(item_unit(it + 1) * CTAS + static_cast<int>(rank)) * 128 + pw * 32;
+          // pull the next item's 32 rows of this warp into L2 now (one 128 B line per lane and step); the register
+          // prefetch below then only has to cover L2 latency
+          const char* nb = reinterpret_cast<const char*>(p.x + next_base * p.d);
+          const long long nbytes = (next_base + 32 <= p.T ? 32LL : (p.T > next_base ? p.T - next_base : 0LL)) * p.d * 4;
+          for (long long o = lane * 128LL; o < nbytes; o += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+        }
+#pragma unroll 1
+        for (int st = 0; st < 8; st += 2) {
+          proj_load_quad(qb, p.x, rbase + (st + 1) * 4, p.T, p.d, nj, sub);
+          proj_process_quad(qa, abuf, r0 + st * 4, (rbase + st * 4) < p.T, p.inv_d, p.eps, nj, sub);
+          if (st + 2 < 8) proj_load_quad(qa, p.x, rbase + (st + 2) * 4, p.T, p.d, nj, sub);
+          else if (next_base >= 0) proj_load_quad(qa, p.x, next_base + rg, p.T, p.d, nj, sub);
+          proj_process_quad(qb, abuf, r0 + (st + 1) * 4, (rbase + (st + 1) * 4) < p.T, p.inv_d, p.eps, nj, sub);
+        }
+      } else {
+        // ---- channel-major source: warp pw owns tokens pw*32 .. +31 (lane = token), loops over channels ----
+        const int r = pw * 32 + lane;
+        const long long tok = m0 + r;
+        const bool ok = tok < p.T;
+        const float* src = p.x + (ok ? tok : 0);
+        if constexpr (AMODE == 1) {
+          // shifted single-pass moments (shift = first channel) keep the variance free of cancellation
+          const float shift = ok ? __ldg(src) : 0.f;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 16
+          for (int c = 0; c < p.d; ++c) {
+            const float vv = ok ? __ldg(src + c * p.src_cs) - shift : 0.f;
+            s1 += vv;
+            s2 += vv * vv;
+          }
+          const float ms = s1 * p.inv_d;
+          const float mean = ms + shift;
+          const float var = fmaxf(s2 * p.inv_d - ms * ms, 0.f);
+          const float rstd = rsqrtf(var + p.eps);
+          const __nv_bfloat16* gsrc = p.gate_cm + (ok ? tok : 0);
+#pragma unroll 8
+          for (int c = 0; c < p.d; c += 2) {
+            float o0 = 0.f, o1 = 0.f;
+            if (ok) {
+              const float v0 = __ldg(src + c * p.src_cs), v1 = __ldg(src + (c + 1) * p.src_cs);
+              const float g0 = __bfloat162float(gsrc[c * p.gate_cs]), g1 = __bfloat162float(gsrc[(c + 1) * p.gate_cs]);
+              o0 = ((v0 - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c)) * g0;
+              o1 = ((v1 - mean) * rstd * __ldg(p.gamma + c + 1) + __ldg(p.beta + c + 1)) * g1;
+            }
+            *reinterpret_cast<uint32_t*>(abuf + (c >> 6) * 16384 + swz128_off(r, (c & 63) >> 3) + (c & 7) * 2) = pack_bf16x2(o0, o1);
+          }
+        } else {
+          const float sc = ok ? (p.scale ? __ldg(p.scale + tok) : p.scale_const) : 0.f;
+#pragma unroll 16
+          for (int c = 0; c < p.d; c += 2) {
+            float o0 = 0.f, o1 = 0.f;
+            if (ok) {
+              o0 = __ldg(src + c * p.src_cs) * sc;
+              o1 = __ldg(src + (c + 1) * p.src_cs) * sc;
+            }
+            *reinterpret_cast<uint32_t*>(abuf + (c >> 6) * 16384 + swz128_off(r, (c & 63) >> 3) + (c & 7) * 2) = pack_bf16x2(o0, o1);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(afull_remote[ab]);
+        else mbar_arrive(&afull_bar[ab]);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace af2

@@ -32,6 +32,9 @@ const char* af2_last_error(void);
 int af2_abi_version(void);
 /* 0 if the current device is compute capability 10.x, AF2_ERR_UNSUPPORTED_DEVICE otherwise */
 int af2_check_device(void);
+/* 2 (default): LN->projection clusters run on the fused CTA-pair kernel; 1: its single-CTA variant; 0: unfused
+ * LayerNorm + GEMM launches (also selectable with the environment variable AF2_PROJ_CTAS, read by af2_check_device) */
+void af2_set_proj_mode(int ctas);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 unsigned long long af2_launch_count(void);
@@ -50,6 +53,10 @@ typedef struct {
   const void* w1; const float* b1;                    /* FeedForward.net.0         packed [n1p, d]  */
   const void* w2; const float* b2;                    /* FeedForward.net.3         [d, hid] , [d]   */
   int bn;                                             /* column tile used for the w1 packing        */
+  /* fused LayerNorm->projection kernel (proj_tc.cuh): every projection of the module that reads LN(x), concatenated,
+   * each segment zero-padded to a multiple of 256 accumulator columns; b_cat is the matching fp32 bias (zeros where none).
+   * NULL -> the unfused LayerNorm + GEMM launches are used.  FeedForward: w_cat == w1, b_cat == b1 (bn must be 256). */
+  const void* w_cat; const float* b_cat;
 } af2_ff_weights;
 int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d, int hidden,
                      void* workspace, long long workspace_bytes, af2_stream_t stream);
@@ -66,6 +73,7 @@ typedef struct {
   const void* w_gate; const float* b_gate;            /* Attention.gating          [I, d], [I]      */
   const void* w_out; const float* b_out;              /* Attention.to_out          [d, I], [d]      */
   const float* w_edge;                                /* edges_to_attn_bias.0      [H, d] fp32/NULL */
+  const void* w_cat; const float* b_cat;              /* [pad256(3I) rows w_qkv | pad256(I) rows w_gate], bias likewise */
 } af2_attn_weights;
 int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask,
                         int B, int h, int wdim, int d, int heads, int dim_head, int row_attn,
@@ -84,6 +92,7 @@ typedef struct {
   const float* on_gamma; const float* on_beta;        /* to_out_norm                                */
   const void* w_out; const float* b_out;              /* to_out                    [d, d], [d]      */
   int bn;
+  const void* w_cat; const float* b_cat;              /* [w_left packed | w_right packed | pad256(d) rows w_ogate]  */
 } af2_trimul_weights;
 int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned char* mask, int B, int N, int d,
                           int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream);
@@ -96,6 +105,7 @@ typedef struct {
   const float* ln_gamma; const float* ln_beta;        /* .norm                                      */
   const void* w_lr; const float* b_lr;                /* [2d, d]: left_proj | right_proj, [2d]      */
   const void* w_out; const float* b_out;              /* proj_out                  [d, d], [d]      */
+  const void* w_cat; const float* b_cat;              /* pad256(2d) rows of w_lr, bias likewise                      */
 } af2_outer_weights;
 int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask,
                    int B, int S, int N, int d, float eps, void* workspace, long long workspace_bytes,
