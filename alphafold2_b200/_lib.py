@@ -14,23 +14,24 @@ vp, ll, ci, cf = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 class FFWeights(C.Structure):
     _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("bn", ci),
-                ("w_cat", vp), ("b_cat", vp)]
+                ("w_cat", vp), ("b_cat", vp), ("w_ext", vp)]
 
 
 class AttnWeights(C.Structure):
     _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_qkv", vp), ("w_gate", vp), ("b_gate", vp),
-                ("w_out", vp), ("b_out", vp), ("w_edge", vp), ("w_cat", vp), ("b_cat", vp)]
+                ("w_out", vp), ("b_out", vp), ("w_edge", vp), ("w_cat", vp), ("b_cat", vp), ("w_ext", vp)]
 
 
 class TriMulWeights(C.Structure):
     _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_left", vp), ("b_left", vp), ("w_right", vp),
                 ("b_right", vp), ("w_ogate", vp), ("b_ogate", vp), ("on_gamma", vp), ("on_beta", vp),
-                ("w_out", vp), ("b_out", vp), ("bn", ci), ("w_cat", vp), ("b_cat", vp)]
+                ("w_out", vp), ("b_out", vp), ("bn", ci), ("w_cat", vp), ("b_cat", vp),
+                ("w_ext", vp), ("w_ext_out", vp)]
 
 
 class OuterWeights(C.Structure):
     _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_lr", vp), ("b_lr", vp), ("w_out", vp), ("b_out", vp),
-                ("w_cat", vp), ("b_cat", vp)]
+                ("w_cat", vp), ("b_cat", vp), ("w_ext", vp), ("w_ext_out", vp)]
 
 
 _SIGNATURES = {

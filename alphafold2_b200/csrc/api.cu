@@ -303,7 +303,37 @@ int launch_layernorm(const LnParams& p, cudaStream_t s) {
   return AF2_OK;
 }
 
+// pair bias <x_raw, w_edge> of T tokens (d % 32 == 0, d <= 256, heads <= 8), else the LayerNorm kernel's bias path
+bool pair_bias_fast_ok(int d, int heads) { return d % 32 == 0 && d <= 256 && heads <= 8; }
+int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_bfloat16* bias_out, int heads, long long bias_hs,
+                     int n_inner, int pitch, cudaStream_t s) {
+  if (T <= 0) return AF2_OK;
+  PairBiasParams p;
+  p.x = x; p.T = T; p.d = d; p.wb = wb; p.bias_out = bias_out; p.heads = heads; p.bias_hs = bias_hs; p.n_inner = n_inner; p.pitch = pitch;
+  const long long need = (T + 31) / 32;                // 8 warps x 4 tokens per block iteration
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  ProfScope ps(s, KC_LAYERNORM, 0.0, (double)T * d * 4 + (double)T * heads * 2);
+  pair_bias_kernel<<<grid, 256, (size_t)heads * d * sizeof(float), s>>>(p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
 int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
+  const long long T = (long long)p.rows * p.n;
+  if (p.pitch == p.n && p.d % 64 == 0 && p.d <= 256 && (T % 4) == 0) {
+    // dense token grid: 64-token tiles, fully coalesced
+    const size_t smem = (size_t)p.d * 64 * sizeof(float) + 8 * 64 * 2 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)T * p.d * (p.mode == 0 ? 8.0 : 6.0));
+    chan_to_token_tile_kernel<<<(unsigned)((T + 63) / 64), 512, smem, s>>>(p, T);
+    CUDA_OK(cudaGetLastError());
+    return AF2_OK;
+  }
   const size_t smem = (size_t)p.d * 33 * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -382,13 +412,13 @@ int g_fuse_tail = 0;   // AF2_FUSE_TAIL=1: triangle / outer-mean tails on the fu
 // x [T, d] += w_out ( A ) + b_out with A produced from the channel-major fp32 contraction output Oc:
 //   mode 1: A = (LN_c(Oc) * gamma + beta) * gate_cm   (triangle multiply tail)   mode 2: A = Oc * scale (outer mean tail)
 int launch_tail(int a_mode, const float* Oc, long long cs_o, long long T, int d, const float* gamma, const float* beta,
-                const void* gate_cm, const float* scale, float scale_const, const void* w_out, const float* b_out, float* x,
+                const void* gate_cm, const float* scale, float scale_const, const void* w_out, const void* w_ext_out, float* x,
                 cudaStream_t s) {
   ProjCall pc;
   memset(&pc, 0, sizeof(pc));
   pc.a_mode = a_mode; pc.x = Oc; pc.T = T; pc.d = d; pc.src_cs = cs_o; pc.gamma = gamma; pc.beta = beta;
   pc.gate_cm = gate_cm; pc.gate_cs = T; pc.scale = scale; pc.scale_const = scale_const;
-  pc.w_cat = w_out; pc.b_cat = b_out; pc.w_rows = d; pc.resid = x; pc.ld_resid = d; pc.nseg = 1;
+  pc.w_cat = w_out; pc.w_ext = w_ext_out; pc.w_rows = d; pc.resid = x; pc.ld_resid = d; pc.nseg = 1;
   pc.seg[0] = ProjOut{1, EK_RESID_F32, d, x, (long long)d};
   return launch_proj(pc, s);
 }
@@ -475,7 +505,7 @@ int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d,
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.nseg = 1;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.nseg = 1;
     pc.seg[0] = ProjOut{n1p / 256, EK_GATED_TOK_GELU, hidden, hbuf, hidden};
     AF2_TRY(launch_proj(pc, s));
   } else {
@@ -539,10 +569,19 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   if (!fused_proj) {
     AF2_TRY(launch_layernorm(lp, s));
   } else if (fuse_bias) {
-    lp.y = nullptr;                       // pair bias only (raw x . w_edge); the LayerNorm itself is fused into the projection
-    AF2_TRY(launch_layernorm(lp, s));
+    // pair bias only (raw x . w_edge); the LayerNorm itself is fused into the projection
+    if (pair_bias_fast_ok(d, heads)) {
+      AF2_TRY(launch_pair_bias(x, T, d, w->w_edge, bias, heads, (long long)n * npad, n, npad, s));
+    } else {
+      lp.y = nullptr;
+      AF2_TRY(launch_layernorm(lp, s));
+    }
   }
-  if (has_bias && !fuse_bias && !pre_bias) {
+  if (has_bias && !fuse_bias && !pre_bias && pair_bias_fast_ok(d, heads)) {
+    for (int b = 0; b < B; ++b)
+      AF2_TRY(launch_pair_bias(edges + (long long)b * n * n * d, (long long)n * n, d, w->w_edge, bias + (long long)b * heads * n * npad,
+                               heads, (long long)n * npad, n, npad, s));
+  } else if (has_bias && !fuse_bias && !pre_bias) {
     for (int b = 0; b < B; ++b) {
       LnParams bp;
       memset(&bp, 0, sizeof(bp));
@@ -558,7 +597,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.nseg = 2;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.nseg = 2;
     pc.seg[0] = ProjOut{(int)((3 * I + 255) / 256), EK_STORE_TOK, (int)(3 * I), qkv, 3 * I};
     pc.seg[1] = ProjOut{(int)((I + 255) / 256), EK_STORE_TOK_SIG, (int)I, gate, I};
     AF2_TRY(launch_proj(pc, s));
@@ -620,7 +659,7 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = mask; pc.nseg = 3;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = mask; pc.nseg = 3;
     const int tl = (d + 127) / 128;
     pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, cs_lr};
     pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, cs_lr};
@@ -669,7 +708,7 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
     AF2_TRY(launch_gemm(c, s));
   }
   if (fused_front && g_fuse_tail)   // LN over channels * out_gate -> to_out -> + residual in one launch
-    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->b_out, x, s);
+    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->w_ext_out, x, s);
   // LN over channels * out_gate -> token-major bf16
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
@@ -726,7 +765,7 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = m; pc.T = Tm; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = msa_mask; pc.nseg = 1;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = msa_mask; pc.nseg = 1;
     pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, cs_lr};
     AF2_TRY(launch_proj(pc, s));
   } else {
@@ -746,7 +785,7 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
     AF2_TRY(launch_gemm(g, s));
   }
   if (fused_front && g_fuse_tail)
-    return launch_tail(2, Oc, cs_o, Tx, d, nullptr, nullptr, nullptr, msa_mask ? scale : nullptr, 1.0f / (float)S, w->w_out, w->b_out, x, s);
+    return launch_tail(2, Oc, cs_o, Tx, d, nullptr, nullptr, nullptr, msa_mask ? scale : nullptr, 1.0f / (float)S, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = B * N; cp.n = N; cp.d = d; cp.mode = 1;
@@ -779,6 +818,9 @@ int af2_pair_bias(const float* x_rows, const float* w_edge, void* bias_out, int 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!x_rows || !w_edge || !bias_out) return fail(AF2_ERR_BAD_ARG, "pair_bias: null argument");
   const int npad = (int)align_up(n, 8);
+  if (pair_bias_fast_ok(d, heads))
+    return launch_pair_bias(x_rows, (long long)rows * n, d, w_edge, static_cast<__nv_bfloat16*>(bias_out), heads, (long long)rows * npad,
+                            n, npad, s);
   LnParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.x = x_rows; bp.T = (long long)rows * n; bp.d = d; bp.eps = 1e-5f;
@@ -810,7 +852,7 @@ int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsi
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = mask; pc.nseg = 3;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = mask; pc.nseg = 3;
     const int tl = (d + 127) / 128;
     pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, chan_stride};
     pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, chan_stride};
@@ -887,7 +929,7 @@ int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc,
     AF2_TRY(launch_gemm(c, s));
   }
   if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && cols % 8 == 0)   // same predicate as af2_triangle_project
-    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->b_out, x, s);
+    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = cp4; cp.rows = rows; cp.n = cols; cp.d = d; cp.mode = 0;
@@ -922,7 +964,7 @@ int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
     pc.a_mode = 0; pc.x = m; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
-    pc.w_cat = w->w_cat; pc.b_cat = w->b_cat; pc.rowmask = msa_mask; pc.nseg = 1;
+    pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = msa_mask; pc.nseg = 1;
     pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, chan_stride};
     return launch_proj(pc, s);
   }
@@ -981,7 +1023,7 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
     AF2_TRY(launch_gemm(g, s));
   }
   if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && N % 4 == 0)
-    return launch_tail(2, Oc, cs_o, T, d, nullptr, nullptr, nullptr, msa_mask_full ? scale : nullptr, 1.0f / (float)S, w->w_out, w->b_out, x, s);
+    return launch_tail(2, Oc, cs_o, T, d, nullptr, nullptr, nullptr, msa_mask_full ? scale : nullptr, 1.0f / (float)S, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = rows; cp.n = N; cp.d = d; cp.mode = 1;

@@ -14,7 +14,8 @@ struct ProjCall {
   const void* gate_cm; long long gate_cs;
   const float* scale; float scale_const;
   const float* wb; void* bias_out; int heads; long long bias_hs; int n_inner, pitch;
-  const void* w_cat; const float* b_cat;
+  const void* w_cat;
+  const void* w_ext;                      // bf16 [tiles * 256][16]: columns 0 / 1 = hi / lo split of the fp32 bias, rest 0
   int w_rows;                             // rows of w_cat (0: every segment padded to whole 256-row tiles)
   const unsigned char* rowmask;
   float* resid; long long ld_resid;       // EK_RESID_F32 segment: residual source (== out for in-place)
@@ -29,8 +30,8 @@ bool proj_dim_ok(int d) { return d % 64 == 0 && d >= 128 && d <= 256; }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int CTAS, int AMODE, int KINDS>
-int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtensorMap& tr, ProjParams& p, double flops,
-                     double bytes, cudaStream_t s) {
+int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtensorMap& tr, const CUtensorMap& tx, ProjParams& p,
+                     double flops, double bytes, cudaStream_t s) {
   using L = ProjSmem<CTAS>;
   static bool configured = false;
   static int max_clusters = 0;
@@ -75,7 +76,7 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, tc[0], tc[1], tc[2], tr, p));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, tc[0], tc[1], tc[2], tr, tx, p));
   return AF2_OK;
 }
 
@@ -89,9 +90,11 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
   p.gate_cm = static_cast<const __nv_bfloat16*>(c.gate_cm); p.gate_cs = c.gate_cs; p.scale = c.scale; p.scale_const = c.scale_const;
   p.wb = c.wb; p.bias_out = static_cast<__nv_bfloat16*>(c.bias_out); p.heads = c.heads; p.bias_hs = c.bias_hs;
   p.n_inner = c.n_inner > 0 ? c.n_inner : 1; p.pitch = c.pitch > 0 ? c.pitch : 1;
-  p.bcat = c.b_cat; p.rowmask = c.rowmask; p.nseg = c.nseg;
+  p.rowmask = c.rowmask; p.nseg = c.nseg;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("AF2_PROJ_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  if (!c.w_ext) return fail(AF2_ERR_BAD_ARG, "proj: bias block (w_ext) missing");
   p.m_tiles = (int)((c.T + 127) / 128);
-  CUtensorMap tc[3], tr, tb;
+  CUtensorMap tc[3], tr, tb, tx;
   int tile0 = 0;
   bool has_resid = false;
   double flops = 0, bytes = (double)c.T * c.d * 4;
@@ -107,18 +110,18 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
     if (!chan) {
       unsigned long long dc[3] = {(unsigned long long)o.out_cols, (unsigned long long)c.T, 1ull};
       unsigned long long sc[2] = {(unsigned long long)o.ld * es, (unsigned long long)o.ld * c.T * es};
-      unsigned bc[3] = {(unsigned)(f32 ? 32 : 64), 128, 1};
-      AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
+      unsigned bc[3] = {(unsigned)(f32 ? 16 : 32), 128, 1};          // 64-byte rows: 8 KB staging buffers
+      AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B, dt));
       if (f32) {
         if (!aligned16(c.resid) || (c.ld_resid * 4) % 16) return fail(AF2_ERR_BAD_ARG, "proj: residual not TMA-describable");
         unsigned long long sr[2] = {(unsigned long long)c.ld_resid * 4, (unsigned long long)c.ld_resid * c.T * 4};
-        AF2_TRY(make_tmap(&tr, c.resid, 3, dc, sr, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
+        AF2_TRY(make_tmap(&tr, c.resid, 3, dc, sr, bc, CU_TENSOR_MAP_SWIZZLE_64B, dt));
         has_resid = true;
       }
     } else {
       unsigned long long dc[3] = {(unsigned long long)c.T, (unsigned long long)o.out_cols, 1ull};
       unsigned long long sc[2] = {(unsigned long long)o.ld * 2, (unsigned long long)o.ld * o.out_cols * 2};
-      unsigned bc[3] = {64, 64, 1};
+      unsigned bc[3] = {64, 32, 1};
       AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
     }
     const int W = (o.kind == EK_GATED_TOK_GELU || o.kind == EK_GATED_CH_SIG) ? 2 : 1;
@@ -128,7 +131,7 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
   for (int i = c.nseg; i < 3; ++i) tc[i] = tc[0];
   if (!has_resid) tr = tc[0];
   p.n_tiles_total = tile0;
-  if (ctas == 2 && tile0 > ProjSmem<2>::BIAS_TILES) return fail(AF2_ERR_BAD_ARG, "proj: %d column tiles exceed the smem bias stage", tile0);
+
   bytes += (double)tile0 * 256 * c.d * 2;
   if (c.a_mode == 1) bytes += (double)c.T * c.d * 2;
   {
@@ -136,13 +139,17 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
     unsigned long long sb[1] = {(unsigned long long)c.d * 2};
     unsigned bb[2] = {64, (unsigned)(256 / ctas)};
     AF2_TRY(make_tmap(&tb, c.w_cat, 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+    unsigned long long dx[2] = {16ull, (unsigned long long)tile0 * 256};
+    unsigned long long sx[1] = {32ull};
+    unsigned bx[2] = {16, (unsigned)(256 / ctas)};
+    AF2_TRY(make_tmap(&tx, c.w_ext, 2, dx, sx, bx, CU_TENSOR_MAP_SWIZZLE_32B));
   }
   int kinds = 0;
   for (int i = 0; i < c.nseg; ++i) kinds |= KBIT(c.seg[i].kind);
 #define AF2_PROJ_DISPATCH(AM, KS)                                                               \
   if (c.a_mode == AM && kinds == KS) {                                                          \
-    if (ctas == 2) return launch_proj_inst<2, AM, KS>(tb, tc, tr, p, flops, bytes, s);          \
-    return launch_proj_inst<1, AM, KS>(tb, tc, tr, p, flops, bytes, s);                         \
+    if (ctas == 2) return launch_proj_inst<2, AM, KS>(tb, tc, tr, tx, p, flops, bytes, s);      \
+    return launch_proj_inst<1, AM, KS>(tb, tc, tr, tx, p, flops, bytes, s);                     \
   }
   AF2_PROJ_DISPATCH(0, PK_ATTN)
   AF2_PROJ_DISPATCH(0, PK_TRI)

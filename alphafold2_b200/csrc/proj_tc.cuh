@@ -23,7 +23,10 @@
 // Warp roles per CTA (512 threads): 0 weight-tile TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator |
 // 3 residual prefetch into the staging buffers (EK_RESID_F32 only) | 4..11 epilogue, two groups of four warps, each
 // group with its own 16 KB staging buffer (TMEM -> regs -> swizzled smem -> TMA store) | 12..15 A producers.
-// Accumulators are double buffered in TMEM (2 x 256 columns per CTA).
+// Accumulators are double buffered in TMEM (2 x 256 columns per CTA).  The bias enters through the tensor core: every
+// column tile starts with one extra K = 16 MMA step  ones[128 x 16] x Bext[256 x 16]^T  (Bext columns 0 / 1 = bf16 hi / lo
+// split of the fp32 bias), so the epilogue neither loads nor adds biases and can hand the accumulator stage back to the
+// MMA as soon as its TMEM loads have landed.
 #pragma once
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
@@ -72,71 +75,39 @@ struct ProjParams {
   long long bias_hs;
   int n_inner, pitch;
   // ---- GEMM / epilogue ----
-  const float* bcat;             // [n_tiles_total * 256] fp32 bias in accumulator-column order (zeros where none)
   const unsigned char* rowmask;  // [T] bool row scale or nullptr (kinds with rowscale)
   int nseg;
   ProjSeg seg[PROJ_MAX_SEG];
   int n_tiles_total;
   int nsplit;                    // column chunks per row unit
   int m_tiles;                   // ceil(T / 128)
+  int dbg;                       // bottleneck hunting (AF2_PROJ_DBG): 1 no staging/store, 2 no producer loads, 4 no math,
+                                 // 8 producer skips everything but the handshake, 16 epilogue releases without TMEM loads
 };
 
 template <int CTAS>
 struct ProjSmem {
-  static constexpr int STAGES = CTAS == 2 ? 3 : 2;                    // the MMA never waited on weight stages with 4
+  static constexpr int STAGES = CTAS == 2 ? 4 : 1;      // (the single-CTA variant is a debugging aid only)
   static constexpr int B_ROWS = 256 / CTAS;
   static constexpr int B_STAGE = B_ROWS * GEMM_BK * 2;               // 16 KB (pair) / 32 KB
-  static constexpr int EPI_BUFS = 2;                                  // one per epilogue warp group
+  static constexpr int EPI_BUFS = 4;                                  // two 8 KB staging buffers per epilogue warp group
+  static constexpr int EPI_BYTES = 8192;                              // 128 rows x 64 B (32 bf16 / 16 fp32 columns)
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = 2 * PROJ_A_BUF;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE;
-  static constexpr int BIAS_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;  // fp32 bias rows of every column tile (pair only)
-  static constexpr int BIAS_TILES = CTAS == 2 ? 12 : 0;
-  static constexpr int BAR_OFF = BIAS_OFF + BIAS_TILES * 1024;
+  static constexpr int AEXT_OFF = EPI_OFF + EPI_BUFS * EPI_BYTES;      // ones block of the bias K-step: 128 rows x 32 B
+  static constexpr int BEXT_BYTES = B_ROWS * 32;                       // bias block of a column tile: rows x 16 bf16
+  // every row of the ones block is identical, so ONE 8-row atom (256 B) is stored and the descriptor's stride between
+  // 8-row groups is 0 (the 4 KB it saves buy the fourth weight stage)
+  static constexpr int AEXT_BYTES = 256;
+  static constexpr int BAR_OFF = AEXT_OFF + AEXT_BYTES;
   static constexpr int TOTAL = BAR_OFF + 512;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can use");
 };
 
-// ---------------------------------------------------------------------------------------------------
-// epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
-//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
-//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
-//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`.  Values are finished in
-//    registers BEFORE the buffer is reclaimed, so the previous TMA store's smem read overlaps the math.
-// ---------------------------------------------------------------------------------------------------
-// bias rows live in shared memory (broadcast LDS) when they fit: global loads here missed L1 (the producers stream the
-// activations through it) and their L2 round trips were the epilogue's critical path
-template <bool SMEM>
-__device__ __forceinline__ float4 proj_bias_ld4(const float* bias, int j) {
-  float4 t4;
-  if constexpr (SMEM) {
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
-                 : "r"(smem_u32(bias) + j * 16));
-  } else {
-    t4 = __ldg(reinterpret_cast<const float4*>(bias) + j);
-  }
-  return t4;
-}
-template <bool SMEM>
-__device__ __forceinline__ void proj_bias_store32(uint32_t taddr, const float* bias) {
-  uint32_t b[32];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t4 = proj_bias_ld4<SMEM>(bias, j);
-    b[4 * j] = __float_as_uint(t4.x); b[4 * j + 1] = __float_as_uint(t4.y);
-    b[4 * j + 2] = __float_as_uint(t4.z); b[4 * j + 3] = __float_as_uint(t4.w);
-  }
-  tmem_st32(taddr, b);
-}
-template <bool SMEM>
-__device__ __forceinline__ void proj_bias_store16(uint32_t taddr, const float* bias) {
-  uint32_t b[16];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 t4 = proj_bias_ld4<SMEM>(bias, j);
-    b[4 * j] = __float_as_uint(t4.x); b[4 * j + 1] = __float_as_uint(t4.y);
-    b[4 * j + 2] = __float_as_uint(t4.z); b[4 * j + 3] = __float_as_uint(t4.w);
-  }
-  tmem_st16(taddr, b);
+// byte offset of 16-byte chunk `chunk` (0..3) of row `row` inside a 64B-swizzled tile whose rows are 64 B
+__device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {
+  return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
 }
 
 // Finish 32 output columns held in registers (u [, g]): activation / gate, row scale, pack to bf16x2.
@@ -163,20 +134,21 @@ __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t*
   for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 
-// 32 packed output columns (tile-local output columns co .. co+31 of the 64-column chunk) -> swizzled staging buffer
+// 32 packed output columns of this thread's row -> 8 KB staging buffer
+//   token layout  : [128 rows][64 B], 64B swizzle (TMA box 32 cols x 128 rows)
+//   channel layout: [32 channels][128 tokens] as two 64-token boxes of 32 rows x 128 B, 128B swizzle
 template <int LAYOUT>
-__device__ __forceinline__ void proj_stage32(uint8_t* eb, int row_in_tile, int half, const uint32_t (&pk)[16]) {
+__device__ __forceinline__ void proj_stage32(uint8_t* eb, int row_in_tile, const uint32_t (&pk)[16]) {
   if constexpr (LAYOUT == LAYOUT_TOKEN) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<uint4*>(eb + swz128_off(row_in_tile, half * 4 + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      *reinterpret_cast<uint4*>(eb + swz64_off(row_in_tile, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   } else {
-    // staging holds [64 channels][128 tokens] as two 64-token boxes of 64 rows x 128 B
-    uint8_t* bx = eb + (row_in_tile >> 6) * 8192;
+    uint8_t* bx = eb + (row_in_tile >> 6) * 4096;
     const uint32_t tl = row_in_tile & 63;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const uint32_t c0 = half * 32 + 2 * j, c1 = c0 + 1;
+      const uint32_t c0 = 2 * j, c1 = c0 + 1;
       *reinterpret_cast<uint16_t*>(bx + c0 * 128 + ((((tl >> 3) ^ (c0 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] & 0xffffu);
       *reinterpret_cast<uint16_t*>(bx + c1 * 128 + ((((tl >> 3) ^ (c1 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] >> 16);
     }
@@ -185,46 +157,44 @@ __device__ __forceinline__ void proj_stage32(uint8_t* eb, int row_in_tile, int h
 
 // ---------------------------------------------------------------------------------------------------
 // epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
-//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
-//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
-//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`.  Values are finished in
-//    registers BEFORE the buffer is reclaimed, so the previous TMA store's smem read overlaps the math.
+// A chunk = 32 bf16 (16 fp32) output columns = one 8 KB staging buffer.  Chunk ec of the CTA goes to epilogue group
+// ec & 1; each group alternates between its own two buffers, so the TMA store of a chunk reads shared memory while the
+// next chunk is produced.  `release` is called by every warp right after the TMEM loads of its LAST chunk of the tile
+// have landed: the accumulator stage goes back to the MMA warp before the math / staging / store of that chunk.
 // ---------------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------------
-// epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
-//  * The accumulator already holds the bias: the epilogue warps preload the NEXT user's bias row into every TMEM column
-//    block right after draining it (tcgen05.st), and the MMA always accumulates -- no bias loads / adds in the hot loop.
-//  * Chunk ec of the CTA goes to epilogue group ec & 1, which owns staging buffer `grp`; a chunk is produced 16 columns
-//    at a time straight into the swizzled staging buffer (low register pressure), then stored with one TMA store.
-// ---------------------------------------------------------------------------------------------------
-template <int EK, bool SB>
+template <int EK, class Release>
 __device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* efull_bar, uint64_t* eempty_bar, uint32_t& ec,
                                                    uint32_t& gc, int grp, bool leader_thread, uint32_t t_acc,
-                                                   const CUtensorMap* tmc, const float* bias_next, float rs, int row_in_tile,
-                                                   int m0, int col0, int ncols) {
+                                                   const CUtensorMap* tmc, float rs, int row_in_tile, int m0, int col0,
+                                                   int ncols, Release release, int dbg) {
   constexpr int mode = EpiTraits<EK>::mode, layout = EpiTraits<EK>::layout;
   constexpr bool out_f32 = (mode == EPI_RESID_F32) || (mode == EPI_STORE_F32);
   constexpr bool gated = (mode == EPI_GATED_BF16);
-  constexpr int CW = out_f32 ? 32 : 64;
-  constexpr int W = gated ? 128 : 256;
+  constexpr int CW = out_f32 ? 16 : 32;
   const int nchunks = (ncols + CW - 1) / CW;
-  uint8_t* eb = epi_base + grp * EPI_BUF_BYTES;
+  // last chunk of this tile that belongs to this group (-1: none -> release immediately)
+  int last_cc = nchunks - 1;
+  if (last_cc >= 0 && ((ec + last_cc) & 1) != static_cast<uint32_t>(grp)) --last_cc;
+  if (last_cc < 0) release();
   for (int cc = 0; cc < nchunks; ++cc, ++ec) {
     if ((ec & 1) != static_cast<uint32_t>(grp)) continue;
+    if (dbg & 16) { if (cc == last_cc) release(); ++gc; continue; }
+    const int bufi = grp * 2 + static_cast<int>(gc & 1);
+    uint8_t* eb = epi_base + bufi * 8192;
     if constexpr (out_f32) {
-      uint32_t u[32];
-      tmem_ld32(t_acc + cc * 32, u);
-      tmem_ld_wait();
-      if (bias_next) proj_bias_store32<SB>(t_acc + cc * 32, bias_next + cc * 32);
-      // reclaim the buffer: the group's previous store must have read it; the residual tile is then prefetched into it
+      uint32_t u[16];
+      tmem_ld16(t_acc + cc * 16, u);
+      // reclaim the buffer (the store issued two chunks ago has read it); the residual tile is then prefetched into it
       if (leader_thread) {
-        tma_store_wait_read<0>();
-        mbar_arrive(&eempty_bar[grp]);
+        tma_store_wait_read<1>();
+        mbar_arrive(&eempty_bar[bufi]);
       }
-      mbar_wait(&efull_bar[grp], gc & 1);
+      tmem_ld_wait();
+      if (cc == last_cc) release();
+      mbar_wait(&efull_bar[bufi], (gc >> 1) & 1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4* sp = reinterpret_cast<float4*>(eb + swz128_off(row_in_tile, j));
+      for (int j = 0; j < 4; ++j) {
+        float4* sp = reinterpret_cast<float4*>(eb + swz64_off(row_in_tile, j));
         float4 o = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
                                __uint_as_float(u[4 * j + 3]));
         if constexpr (mode == EPI_RESID_F32) {
@@ -234,59 +204,28 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* 
         *sp = o;
       }
     } else {
-      // All TMEM loads of the chunk are issued up front (one round trip of latency per chunk instead of four), the
-      // buffer reclaim overlaps them, and the bias of the stage's next user goes back with asynchronous tcgen05.st.
-      if constexpr (gated) {
-        uint32_t u0[32], g0[32];
-        tmem_ld32(t_acc + cc * 64, u0);
-        tmem_ld32(t_acc + 128 + cc * 64, g0);
-        if (leader_thread) tma_store_wait_read<0>();
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-        tmem_ld_wait();
-        uint32_t u1[32], g1[32];
-        tmem_ld32(t_acc + cc * 64 + 32, u1);            // second half in flight while the first is finished
-        tmem_ld32(t_acc + 128 + cc * 64 + 32, g1);
-        {
-          uint32_t pk[16];
-          proj_finish32<EK>(u0, g0, rs, pk);
-          proj_stage32<layout>(eb, row_in_tile, 0, pk);
-        }
-        tmem_ld_wait();
-        {
-          uint32_t pk[16];
-          proj_finish32<EK>(u1, g1, rs, pk);
-          proj_stage32<layout>(eb, row_in_tile, 1, pk);
-        }
-        if (bias_next) {
-          proj_bias_store32<SB>(t_acc + cc * 64, bias_next + cc * 64);
-          proj_bias_store32<SB>(t_acc + cc * 64 + 32, bias_next + cc * 64 + 32);
-          proj_bias_store32<SB>(t_acc + 128 + cc * 64, bias_next + 128 + cc * 64);
-          proj_bias_store32<SB>(t_acc + 128 + cc * 64 + 32, bias_next + 128 + cc * 64 + 32);
-        }
-      } else {
-        uint32_t u0[32], u1[32];
-        tmem_ld32(t_acc + cc * 64, u0);
-        tmem_ld32(t_acc + cc * 64 + 32, u1);
-        if (leader_thread) tma_store_wait_read<0>();
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-        tmem_ld_wait();
-        if (bias_next) {
-          proj_bias_store32<SB>(t_acc + cc * 64, bias_next + cc * 64);
-          proj_bias_store32<SB>(t_acc + cc * 64 + 32, bias_next + cc * 64 + 32);
-        }
-        {
-          uint32_t pk[16];
-          proj_finish32<EK>(u0, nullptr, rs, pk);
-          proj_stage32<layout>(eb, row_in_tile, 0, pk);
-        }
-        {
-          uint32_t pk[16];
-          proj_finish32<EK>(u1, nullptr, rs, pk);
-          proj_stage32<layout>(eb, row_in_tile, 1, pk);
+      uint32_t pk[16];
+      {
+        uint32_t u[32];
+        tmem_ld32(t_acc + cc * 32, u);
+        if constexpr (gated) {
+          uint32_t g[32];
+          tmem_ld32(t_acc + 128 + cc * 32, g);
+          tmem_ld_wait();
+          if (cc == last_cc) release();
+          proj_finish32<EK>(u, g, rs, pk);
+        } else {
+          tmem_ld_wait();
+          if (cc == last_cc) release();
+          proj_finish32<EK>(u, nullptr, rs, pk);
         }
       }
+      if (dbg & 1) { if (pk[0] == 0x12345678u && pk[3] == 0x1u) release(); ++gc; continue; }
+      // the store that used this buffer two chunks ago must have read it (one newer store may still be in flight)
+      if (leader_thread) tma_store_wait_read<1>();
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      proj_stage32<layout>(eb, row_in_tile, pk);
     }
     fence_proxy_async_smem();
     if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -295,19 +234,12 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* 
       if constexpr (layout == LAYOUT_TOKEN) {
         tma_store_3d(tmc, eb, col0 + cc * CW, m0, 0);
       } else {
-        tma_store_3d(tmc, eb, m0, col0 + cc * 64, 0);
-        tma_store_3d(tmc, eb + 8192, m0 + 64, col0 + cc * 64, 0);
+        tma_store_3d(tmc, eb, m0, col0 + cc * 32, 0);
+        tma_store_3d(tmc, eb + 4096, m0 + 64, col0 + cc * 32, 0);
       }
       tma_store_commit();
     }
     ++gc;
-  }
-  // output columns clipped away (ragged last tile of a segment) are read by nobody: group 0 re-initialises them
-  if (bias_next && grp == 0) {
-    for (int c = nchunks * CW; c < W; c += 32) {
-      proj_bias_store32<SB>(t_acc + c, bias_next + c);
-      if constexpr (gated) proj_bias_store32<SB>(t_acc + 128 + c, bias_next + 128 + c);
-    }
   }
 }
 
@@ -376,7 +308,8 @@ template <int CTAS, int AMODE, int KINDS>
 __global__ void __launch_bounds__(PROJ_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
                const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ProjParams p) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmX,
+               const __grid_constant__ ProjParams p) {
   using L = ProjSmem<CTAS>;
   constexpr int STAGES = L::STAGES;
   constexpr bool HAS_RESID = (KINDS & KBIT(EK_RESID_F32)) != 0;
@@ -390,9 +323,9 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;                                // [STAGES] weight stage consumed
   uint64_t* tfull_bar = empty_bar + STAGES;                               // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                                   // [2] accumulator drained (leader's)
-  uint64_t* efull_bar = tempty_bar + 2;                                   // [2] residual tile landed in group buffer
-  uint64_t* eempty_bar = efull_bar + 2;                                   // [2] group buffer reclaimed
-  uint64_t* afull_bar = eempty_bar + 2;                                   // [2] A buffer produced (leader's)
+  uint64_t* efull_bar = tempty_bar + 2;                                   // [4] residual tile landed in staging buffer
+  uint64_t* eempty_bar = efull_bar + 4;                                   // [4] staging buffer reclaimed
+  uint64_t* afull_bar = eempty_bar + 4;                                   // [2] A buffer produced (leader's)
   uint64_t* aempty_bar = afull_bar + 2;                                   // [2] A buffer consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
@@ -406,6 +339,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmX);
     prefetch_tmap(&tmC0);
   }
   if (warp == 1 && lane == 0) {
@@ -418,6 +352,8 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       mbar_init(&tempty_bar[s], 8 * CTAS);
       mbar_init(&afull_bar[s], 4 * CTAS);
       mbar_init(&aempty_bar[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&efull_bar[s], 1);
       mbar_init(&eempty_bar[s], 1);
     }
@@ -427,14 +363,11 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     if constexpr (CTAS == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
     else tmem_alloc(tmem_slot, TMEM_COLS);
   }
-  // stage the bias rows of every column tile in shared memory (all threads; visible after the sync below)
-  constexpr bool sbias = L::BIAS_TILES > 0;       // host guarantees n_tiles_total <= BIAS_TILES for the pair kernel
-  if constexpr (sbias) {
-    float4* dst = reinterpret_cast<float4*>(smem + L::BIAS_OFF);
-    const float4* src = reinterpret_cast<const float4*>(p.bcat);
-    for (int i = threadIdx.x; i < p.n_tiles_total * 64; i += PROJ_THREADS) dst[i] = __ldg(src + i);
-  }
-  const float* bias_base = sbias ? reinterpret_cast<const float*>(smem + L::BIAS_OFF) : p.bcat;
+  // ones block of the bias K-step (SW32 rows of 32 B; both 16-byte chunks identical, so the chunk swizzle is irrelevant):
+  // A_ext[r][k] = 1 for k in {0, 1, 8, 9}; the bias block has data in columns 0 / 1 only
+  for (int i = threadIdx.x; i < L::AEXT_BYTES / 16; i += PROJ_THREADS)
+    *reinterpret_cast<uint4*>(smem + L::AEXT_OFF + i * 16) = make_uint4(0x3f803f80u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all();
   else __syncthreads();
@@ -470,15 +403,18 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       for (int it = 0; it < my_items; ++it) {
         const int ch = item_chunk(it);
         for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt) {
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = -1; kb < nkb; ++kb) {                 // kb = -1: the tile's bias block (rows x 16 bf16)
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sb = smem + L::B_OFF + stage * L::B_STAGE;
+            const CUtensorMap* tm = kb < 0 ? &tmX : &tmB;
+            const int bytes = kb < 0 ? L::BEXT_BYTES : L::B_STAGE;
+            const int c0 = kb < 0 ? 0 : kb * GEMM_BK;
             if constexpr (CTAS == 2) {
-              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::B_STAGE);
-              tma_load_2d_pair(sb, &tmB, full_remote[stage], kb * GEMM_BK, nt * 256 + static_cast<int>(rank) * L::B_ROWS);
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
+              tma_load_2d_pair(sb, tm, full_remote[stage], c0, nt * 256 + static_cast<int>(rank) * L::B_ROWS);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], L::B_STAGE);
-              tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * 256);
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              tma_load_2d(sb, tm, &full_bar[stage], c0, nt * 256);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -501,21 +437,29 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const int t1 = chunk_t1(ch);
         for (int nt = chunk_t0(ch); nt < t1; ++nt, ++tcnt) {
           const int acc = tcnt & 1;
-          mbar_wait(&tempty_bar[acc], (tcnt >> 1) & 1);     // completion #k: bias preloaded (k = 0) / stage drained + preloaded
+          mbar_wait(&tempty_bar[acc], ((tcnt >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 256;
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = -1; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t sa = sa0 + kb * 16384;
               const uint32_t sb = smem_u32(smem + L::B_OFF + stage * L::B_STAGE);
+              if (kb < 0) {
+                // accumulator = ones x bias block (SW32 operands: 32-byte rows, 8-row atoms 256 B apart)
+                const uint64_t adesc = umma_smem_desc(smem_u32(smem + L::AEXT_OFF), 16, 0, SWZ_32);   // SBO 0: rows aliased
+                const uint64_t bdesc = umma_smem_desc(sb, 16, 256, SWZ_32);
+                if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 0u);
+                else umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);
+              } else {
+                const uint32_t sa = sa0 + kb * 16384;
 #pragma unroll
-              for (int k = 0; k < GEMM_BK / 16; ++k) {
-                const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, 1024, SWZ_128);
-                const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, 1024, SWZ_128);
-                if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 1u);   // accumulator starts at the bias
-                else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                  const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, 1024, SWZ_128);
+                  const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, 1024, SWZ_128);
+                  if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, 1u);
+                  else umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                }
               }
               if constexpr (CTAS == 2) {
                 umma_commit_pair(&empty_bar[stage], 3);
@@ -549,13 +493,14 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             const ProjSeg& sg = p.seg[seg_of(nt)];
             const int col0 = (nt - sg.tile0) * 256;
             const int ncols = min(256, sg.out_cols - col0);
-            const int nchunks = ncols > 0 ? (ncols + 31) / 32 : 0;
+            const int nchunks = ncols > 0 ? (ncols + 15) / 16 : 0;
             for (int cc = 0; cc < nchunks; ++cc, ++ec) {
               const int g = ec & 1;
               const uint32_t k = gcnt[g]++;
-              mbar_wait(&eempty_bar[g], k & 1);                    // group g reclaimed its buffer for its k-th chunk
-              mbar_arrive_expect_tx(&efull_bar[g], EPI_BUF_BYTES);
-              tma_load_3d(smem + L::EPI_OFF + g * EPI_BUF_BYTES, &tmR, &efull_bar[g], col0 + cc * 32, m0, 0);
+              const int bufi = g * 2 + static_cast<int>(k & 1);
+              mbar_wait(&eempty_bar[bufi], (k >> 1) & 1);          // group g reclaimed this buffer for its k-th chunk
+              mbar_arrive_expect_tx(&efull_bar[bufi], L::EPI_BYTES);
+              tma_load_3d(smem + L::EPI_OFF + bufi * L::EPI_BYTES, &tmR, &efull_bar[bufi], col0 + cc * 16, m0, 0);
             }
           }
         }
@@ -572,36 +517,6 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     tempty_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
     uint8_t* epi_base = smem + L::EPI_OFF;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    // n-tile index of the k-th tile of this cluster's sequence (or -1): items are walked in order, each with its chunk
-    auto tile_at = [&](int it, int nt, int steps, int& nt_out) {
-      while (it < my_items) {
-        const int t1 = chunk_t1(item_chunk(it));
-        if (nt + steps < t1) { nt_out = nt + steps; return true; }
-        steps -= (t1 - nt);
-        ++it;
-        if (it < my_items) nt = chunk_t0(item_chunk(it));
-      }
-      return false;
-    };
-    // prime both accumulator stages with the bias of the first two tiles (group g preloads column blocks g, g+2, ...)
-    if (my_items > 0) {
-      for (int a = 0; a < 2; ++a) {
-        int ntp;
-        if (tile_at(0, chunk_t0(item_chunk(0)), a, ntp)) {
-          const float* bp = bias_base + static_cast<long long>(ntp) * 256;
-          for (int c = grp * 32; c < 256; c += 64) proj_bias_store32<sbias>(tmem_base + a * 256 + lane_sel + c, bp + c);
-        }
-      }
-      tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      for (int a = 0; a < 2; ++a) {
-        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_remote[a]);
-        else mbar_arrive(&tempty_bar[a]);
-      }
-    }
     uint32_t ec = 0, gc = 0, tcnt = 0;
     for (int it = 0; it < my_items; ++it) {
       const int unit = item_unit(it), ch = item_chunk(it);
@@ -615,17 +530,24 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const int W = proj_tile_width(sg.kind);
         const int col0 = (nt - sg.tile0) * W;
         const int ncols = min(W, sg.out_cols - col0);
-        int nt2;
-        const float* bias_next = tile_at(it, nt, 2, nt2) ? bias_base + static_cast<long long>(nt2) * 256 : nullptr;
         const CUtensorMap* tmc = sg.map == 0 ? &tmC0 : (sg.map == 1 ? &tmC1 : &tmC2);
         mbar_wait(&tfull_bar[acc], (tcnt >> 1) & 1);
         tc_fence_after();
         const uint32_t t_acc = tmem_base + acc * 256 + lane_sel;
+        // hand the accumulator stage back: this warp's TMEM loads of the tile have landed (8 * CTAS warps arrive)
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_remote[acc]);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
+        };
 #define AF2_PROJ_CASE(EKV)                                                                                               \
   if constexpr ((KINDS & KBIT(EKV)) != 0) {                                                                              \
     if (sg.kind == EKV)                                                                                                  \
-      proj_epilogue_tile<EKV, sbias>(epi_base, efull_bar, eempty_bar, ec, gc, grp, leader_thread, t_acc, tmc,            \
-                                     bias_next, rs, row_in_tile, m0, col0, ncols > 0 ? ncols : 0);                       \
+      proj_epilogue_tile<EKV>(epi_base, efull_bar, eempty_bar, ec, gc, grp, leader_thread, t_acc, tmc, rs, row_in_tile,  \
+                              m0, col0, ncols > 0 ? ncols : 0, release, p.dbg);                                          \
   }
         AF2_PROJ_CASE(EK_STORE_TOK)
         AF2_PROJ_CASE(EK_STORE_TOK_SIG)
@@ -635,13 +557,6 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         AF2_PROJ_CASE(EK_GATED_CH_SIG)
         AF2_PROJ_CASE(EK_RESID_F32)
 #undef AF2_PROJ_CASE
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_remote[acc]);
-          else mbar_arrive(&tempty_bar[acc]);
-        }
       }
     }
     if (leader_thread) tma_store_wait_read<0>();
@@ -683,6 +598,12 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         }
 #pragma unroll 1
         for (int st = 0; st < 8; st += 2) {
+          if (p.dbg & 8) break;
+          if (p.dbg & 2) {
+            proj_process_quad(qa, abuf, r0 + st * 4, true, p.inv_d, p.eps, nj, sub);
+            proj_process_quad(qa, abuf, r0 + (st + 1) * 4, true, p.inv_d, p.eps, nj, sub);
+            continue;
+          }
           proj_load_quad(qb, p.x, rbase + (st + 1) * 4, p.T, p.d, nj, sub);
           proj_process_quad(qa, abuf, r0 + st * 4, (rbase + st * 4) < p.T, p.inv_d, p.eps, nj, sub);
           if (st + 2 < 8) proj_load_quad(qa, p.x, rbase + (st + 2) * 4, p.T, p.d, nj, sub);

@@ -184,6 +184,149 @@ __global__ void __launch_bounds__(256) chan_to_token_kernel(const ChanLnParams p
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pair bias of axial / triangle attention (alphafold2.py:214-217, 245-247):
+//   bias[h][(t / n_inner) * pitch + t % n_inner] = <x_raw[t, :], Wb[h, :]>      bf16, H <= 8 heads per pass, d <= 256
+// Eight lanes share a token (4 tokens per warp instruction): 128-byte coalesced row segments, w_edge staged in shared
+// memory, 3-level shuffle reductions.  Streams x once (HBM bound).
+// ------------------------------------------------------------------------------------------------
+struct PairBiasParams {
+  const float* x;
+  long long T;
+  int d;
+  const float* wb;          // [H, d]
+  __nv_bfloat16* bias_out;  // [H][bias_hs]
+  int heads;
+  long long bias_hs;
+  int n_inner, pitch;
+};
+
+__global__ void __launch_bounds__(256) pair_bias_kernel(const PairBiasParams p) {
+  extern __shared__ float wsm[];                       // [heads][d]
+  for (int i = threadIdx.x; i < p.heads * p.d; i += blockDim.x) wsm[i] = __ldg(p.wb + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, rg = lane >> 3;
+  const int nj = p.d >> 5;                             // float4 chunks per lane
+  const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long t0 = warp_global * 4; t0 < p.T; t0 += nwarps * 4) {
+    const long long t = t0 + rg;
+    const bool live = t < p.T;
+    float4 v[8];
+    const float4* xr = reinterpret_cast<const float4*>(p.x + (live ? t : 0) * p.d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (live && j < nj) ? __ldg(xr + j * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      acc[h] = 0.f;
+      if (h < p.heads) {
+        const float4* wr = reinterpret_cast<const float4*>(wsm + h * p.d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nj) {
+            const float4 w = wr[j * 8 + sub];
+            acc[h] += v[j].x * w.x + v[j].y * w.y + v[j].z * w.z + v[j].w * w.w;
+          }
+        }
+      }
+    }
+    // reduce over the 8 lanes of the token: after xor-4 / 2 / 1 halving, lane `sub` holds head `sub`
+    float r4[4], r2[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool hi = sub & 4;
+      const float mine = hi ? acc[4 + k] : acc[k], other = hi ? acc[k] : acc[4 + k];
+      r4[k] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const bool hi = sub & 2;
+      const float mine = hi ? r4[2 + k] : r4[k], other = hi ? r4[k] : r4[2 + k];
+      r2[k] = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    }
+    const bool hi1 = sub & 1;
+    const float res = (hi1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, hi1 ? r2[0] : r2[1], 1);
+    // lane sub now holds head index: bit2 = sub&4 -> +4, bit1 -> +2, bit0 -> +1  == sub
+    if (live && sub < p.heads) {
+      const long long off = (t / p.n_inner) * p.pitch + (t % p.n_inner);
+      p.bias_out[sub * p.bias_hs + off] = __float2bfloat16(res);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel-major fp32 contraction output -> token-major bf16 operand, tile version (replaces chan_to_token_kernel when the
+// token grid is dense, pitch == n):  a CTA (512 threads) owns 64 consecutive tokens x all d channels:
+//   phase 1: 256-byte coalesced row segments src[c][t0 .. t0+63] -> shared tile [d][64] (16 independent 16-byte loads per thread)
+//   phase 2: thread = (token, 32-channel slice): LayerNorm over channels (mode 0) or scale (mode 1), gate, 64-byte bf16 stores
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) chan_to_token_tile_kernel(const ChanLnParams p, long long T) {
+  extern __shared__ float tile[];                      // [d][64] followed by [8][64][2] partial moments
+  const long long t0 = static_cast<long long>(blockIdx.x) * 64;
+  const int tid = threadIdx.x;
+  // ---- phase 1 ----
+  {
+    const int q = tid & 15;                            // float4 index inside the 64-token segment
+    const bool ok = (t0 + q * 4) < T;                  // T % 4 == 0 (pitch multiple of 4)
+    for (int c = tid >> 4; c < p.d; c += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = __ldg(reinterpret_cast<const float4*>(p.src + static_cast<long long>(c) * p.chan_stride + t0) + q);
+      reinterpret_cast<float4*>(tile + c * 64)[q] = v;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2 ----
+  const int tok = tid & 63, slice = tid >> 6;          // 8 slices of d/8 channels
+  const int cpt = p.d >> 3;                            // channels per thread (<= 32)
+  const long long token = t0 + tok;
+  float* part = tile + p.d * 64;
+  float mean = 0.f, rstd = 1.f;
+  if (p.mode == 0) {
+    float s1 = 0.f;
+    for (int i = 0; i < cpt; ++i) s1 += tile[(slice * cpt + i) * 64 + tok];
+    part[(slice * 64 + tok) * 2] = s1;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[(k * 64 + tok) * 2];
+    mean = tot / p.d;
+    float s2 = 0.f;
+    for (int i = 0; i < cpt; ++i) {
+      const float a = tile[(slice * cpt + i) * 64 + tok] - mean;
+      s2 += a * a;
+    }
+    part[(slice * 64 + tok) * 2 + 1] = s2;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) var += part[(k * 64 + tok) * 2 + 1];
+    rstd = rsqrtf(var / p.d + p.eps);
+  }
+  if (token < T) {
+    const int c0 = slice * cpt;
+    const float sc = (p.mode == 1) ? (p.scale ? __ldg(p.scale + token) : p.scale_const) : 1.f;
+    for (int i = 0; i < cpt; i += 8) {
+      float o[8];
+      if (p.mode == 0) {
+        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(p.gate + token * p.d + c0 + i));
+        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + i + k;
+          const float g = (k & 1) ? bf16hi_to_f32(gw[k >> 1]) : bf16lo_to_f32(gw[k >> 1]);
+          o[k] = ((tile[c * 64 + tok] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c)) * g;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = tile[(c0 + i + k) * 64 + tok] * sc;
+      }
+      *reinterpret_cast<uint4*>(p.y + token * p.d + c0 + i) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // OuterMean normaliser (quirk Q3, alphafold2.py:345-347):
 //   scale[b][i][j] = 1 / (S * (sum_s mask[b,s,i] * mask[b,s,j] + eps))      (fp32, like the reference)
 // ------------------------------------------------------------------------------------------------

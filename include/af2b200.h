@@ -57,6 +57,7 @@ typedef struct {
    * each segment zero-padded to a multiple of 256 accumulator columns; b_cat is the matching fp32 bias (zeros where none).
    * NULL -> the unfused LayerNorm + GEMM launches are used.  FeedForward: w_cat == w1, b_cat == b1 (bn must be 256). */
   const void* w_cat; const float* b_cat;
+  const void* w_ext;   /* bias block of the fused kernel: bf16 [rows(w_cat)][16], columns 0 / 1 = hi / lo bf16 split of b_cat */
 } af2_ff_weights;
 int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d, int hidden,
                      void* workspace, long long workspace_bytes, af2_stream_t stream);
@@ -74,6 +75,7 @@ typedef struct {
   const void* w_out; const float* b_out;              /* Attention.to_out          [d, I], [d]      */
   const float* w_edge;                                /* edges_to_attn_bias.0      [H, d] fp32/NULL */
   const void* w_cat; const float* b_cat;              /* [pad256(3I) rows w_qkv | pad256(I) rows w_gate], bias likewise */
+  const void* w_ext;
 } af2_attn_weights;
 int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask,
                         int B, int h, int wdim, int d, int heads, int dim_head, int row_attn,
@@ -93,6 +95,7 @@ typedef struct {
   const void* w_out; const float* b_out;              /* to_out                    [d, d], [d]      */
   int bn;
   const void* w_cat; const float* b_cat;              /* [w_left packed | w_right packed | pad256(d) rows w_ogate]  */
+  const void* w_ext; const void* w_ext_out;           /* bias blocks of w_cat and (fused tail) of w_out              */
 } af2_trimul_weights;
 int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned char* mask, int B, int N, int d,
                           int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream);
@@ -106,6 +109,7 @@ typedef struct {
   const void* w_lr; const float* b_lr;                /* [2d, d]: left_proj | right_proj, [2d]      */
   const void* w_out; const float* b_out;              /* proj_out                  [d, d], [d]      */
   const void* w_cat; const float* b_cat;              /* pad256(2d) rows of w_lr, bias likewise                      */
+  const void* w_ext; const void* w_ext_out;
 } af2_outer_weights;
 int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask,
                    int B, int S, int N, int d, float eps, void* workspace, long long workspace_bytes,
