@@ -55,7 +55,8 @@ struct AttnSmem {
   static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
   static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
   static constexpr int QV_OFF = L_OFF + 2 * 128 * 4;    // query-mask bytes [2][128]
-  static constexpr int TOTAL = QV_OFF + 2 * 128 + 1024;
+  static constexpr int KF_OFF = QV_OFF + 2 * 128;       // [2] per-stage flag: some key of the block is masked / padding
+  static constexpr int TOTAL = KF_OFF + 16 + 1024;
 };
 
 // tmQ/tmK/tmV: 4-D maps over the projection buffer, dims (e [DH], i [n], h [heads], b' [nbatch]),
@@ -91,6 +92,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
   float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
   uint8_t* qvbuf = smem + L::QV_OFF;                          // [2][128]
+  uint32_t* kflag = reinterpret_cast<uint32_t*>(smem + L::KF_OFF);   // [2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,7 +241,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (qi < p.n && p.mask[b * p.mask_sb + qi * p.mask_si] == 0) qv &= ~(0xffu << (8 * i));
           }
         }
+        const bool some_masked = __any_sync(0xffffffffu, (kb[0] != 0.f) | (kb[1] != 0.f) | (kb[2] != 0.f) | (kb[3] != 0.f));
         mbar_wait(&kb_empty[st], ((g >> 1) & 1) ^ 1);
+        if (lane == 0) kflag[st] = some_masked ? 1u : 0u;
         *reinterpret_cast<float4*>(keyb + st * 128 + lane * 4) = make_float4(kb[0], kb[1], kb[2], kb[3]);
         if (j == 0) *reinterpret_cast<uint32_t*>(qvbuf + (it & 1) * 128 + lane * 4) = qv;
         __syncwarp();
@@ -292,20 +296,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // logits (log2 domain) = s + bias + keyterm
       const uint8_t* sbias = smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES + L::V_BYTES + hk * 16384;
       const float* kbs = keyb + st * 128 + hk * 64;
+      const bool keys_masked = kflag[st] != 0u;      // block-uniform: most blocks have every key usable
       float mx0 = NEG_INF, mx1 = NEG_INF;
+      if (p.has_bias) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {         // 8 chunks of 8 keys
-        if (p.has_bias) {
+        for (int c = 0; c < 8; ++c) {       // 8 chunks of 8 keys
           const uint4 raw = *reinterpret_cast<const uint4*>(sbias + swz128_off(r, c));
           s[c * 8 + 0] += bf16lo_to_f32(raw.x); s[c * 8 + 1] += bf16hi_to_f32(raw.x);
           s[c * 8 + 2] += bf16lo_to_f32(raw.y); s[c * 8 + 3] += bf16hi_to_f32(raw.y);
           s[c * 8 + 4] += bf16lo_to_f32(raw.z); s[c * 8 + 5] += bf16hi_to_f32(raw.z);
           s[c * 8 + 6] += bf16lo_to_f32(raw.w); s[c * 8 + 7] += bf16hi_to_f32(raw.w);
         }
-        const float4 k0 = *reinterpret_cast<const float4*>(kbs + c * 8);
-        const float4 k1 = *reinterpret_cast<const float4*>(kbs + c * 8 + 4);
-        s[c * 8 + 0] += k0.x; s[c * 8 + 1] += k0.y; s[c * 8 + 2] += k0.z; s[c * 8 + 3] += k0.w;
-        s[c * 8 + 4] += k1.x; s[c * 8 + 5] += k1.y; s[c * 8 + 6] += k1.z; s[c * 8 + 7] += k1.w;
+      }
+      if (keys_masked) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 k0 = *reinterpret_cast<const float4*>(kbs + c * 8);
+          const float4 k1 = *reinterpret_cast<const float4*>(kbs + c * 8 + 4);
+          s[c * 8 + 0] += k0.x; s[c * 8 + 1] += k0.y; s[c * 8 + 2] += k0.z; s[c * 8 + 3] += k0.w;
+          s[c * 8 + 4] += k1.x; s[c * 8 + 5] += k1.y; s[c * 8 + 6] += k1.z; s[c * 8 + 7] += k1.w;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&kb_empty[st]);
@@ -320,7 +330,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       mxbuf[hk * 128 + r] = fmaxf(mx0, mx1);
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // only the two warps sharing these 32 rows
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), mxbuf[(hk ^ 1) * 128 + r]));
+      float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), mxbuf[(hk ^ 1) * 128 + r]));
+      // Lazy rescaling: the running maximum only has to be SOME upper bound up to a factor that neither overflows bf16 P nor
+      // the fp32 sums.  While the block maximum exceeds it by <= 2^8 (log2 domain) we keep the stale one and skip the
+      // TMEM round trip of O; the decision is made per warp (both warps sharing these rows see identical values).
+      bool rescale = true;
+      if (j > 0) {
+        rescale = __any_sync(0xffffffffu, m_new > m_run + 8.0f);
+        if (!rescale) m_new = m_run;
+      }
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
       const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
       float ls0 = 0.f, ls1 = 0.f;
@@ -338,7 +356,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j > 0) {
         mbar_wait(pv_done, (g - 1) & 1);
         tc_fence_after();
-        if (o_owner) {
+        if (o_owner && rescale) {
           uint32_t o[32];
           tmem_ld32(tmem_base + o_col + lane_sel, o);
           tmem_ld_wait();

@@ -175,7 +175,8 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* 
   // last chunk of this tile that belongs to this group (-1: none -> release immediately)
   int last_cc = nchunks - 1;
   if (last_cc >= 0 && ((ec + last_cc) & 1) != static_cast<uint32_t>(grp)) --last_cc;
-  if (last_cc < 0) release();
+  if (dbg & 256) { if (last_cc >= 0) release(); last_cc = -2; }     // timing experiment: hand the stage back before draining it
+  if (last_cc == -1) release();
   for (int cc = 0; cc < nchunks; ++cc, ++ec) {
     if ((ec & 1) != static_cast<uint32_t>(grp)) continue;
     if (dbg & 16) { if (cc == last_cc) release(); ++gc; continue; }
