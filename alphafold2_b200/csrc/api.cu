@@ -407,22 +407,6 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
 
 #include "proj_launch.inl"
 
-int g_fuse_tail = 0;   // AF2_FUSE_TAIL=1: triangle / outer-mean tails on the fused kernel (a_mode 1 / 2)
-
-// x [T, d] += w_out ( A ) + b_out with A produced from the channel-major fp32 contraction output Oc:
-//   mode 1: A = (LN_c(Oc) * gamma + beta) * gate_cm   (triangle multiply tail)   mode 2: A = Oc * scale (outer mean tail)
-int launch_tail(int a_mode, const float* Oc, long long cs_o, long long T, int d, const float* gamma, const float* beta,
-                const void* gate_cm, const float* scale, float scale_const, const void* w_out, const void* w_ext_out, float* x,
-                cudaStream_t s) {
-  ProjCall pc;
-  memset(&pc, 0, sizeof(pc));
-  pc.a_mode = a_mode; pc.x = Oc; pc.T = T; pc.d = d; pc.src_cs = cs_o; pc.gamma = gamma; pc.beta = beta;
-  pc.gate_cm = gate_cm; pc.gate_cs = T; pc.scale = scale; pc.scale_const = scale_const;
-  pc.w_cat = w_out; pc.w_ext = w_ext_out; pc.w_rows = d; pc.resid = x; pc.ld_resid = d; pc.nseg = 1;
-  pc.seg[0] = ProjOut{1, EK_RESID_F32, d, x, (long long)d};
-  return launch_proj(pc, s);
-}
-
 int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)sm_count() * 8;
@@ -466,11 +450,7 @@ long long af2_profile_read(int cls, double* ms, double* flops, double* bytes) {
   return n;
 }
 
-void af2_set_proj_mode(int ctas) {
-  g_fuse_tail = (ctas >= 10) ? 1 : 0;            // 1x: additionally run the triangle / outer-mean tails on the fused kernel
-  ctas %= 10;
-  g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : ctas);
-}
+void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : ctas); }
 
 int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
@@ -504,7 +484,7 @@ int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d,
     // fused LayerNorm -> Linear -> GEGLU (A-stationary CTA-pair kernel)
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = x; pc.T = tokens; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.nseg = 1;
     pc.seg[0] = ProjOut{n1p / 256, EK_GATED_TOK_GELU, hidden, hbuf, hidden};
     AF2_TRY(launch_proj(pc, s));
@@ -596,7 +576,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
     // one launch: LayerNorm (+ pair bias) -> [q | k | v] and sigmoid(gating)
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = x; pc.T = T; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.nseg = 2;
     pc.seg[0] = ProjOut{(int)((3 * I + 255) / 256), EK_STORE_TOK, (int)(3 * I), qkv, 3 * I};
     pc.seg[1] = ProjOut{(int)((I + 255) / 256), EK_STORE_TOK_SIG, (int)I, gate, I};
@@ -658,13 +638,12 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
   if (fused_front) {
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = x; pc.T = T; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = x; pc.T = T; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = mask; pc.nseg = 3;
     const int tl = (d + 127) / 128;
     pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, cs_lr};
     pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, cs_lr};
-    if (g_fuse_tail) pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_CH_SIG, d, gate, T};   // channel-major gate for the fused tail
-    else pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
+    pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
     AF2_TRY(launch_proj(pc, s));
   }
   LnParams lp;
@@ -707,8 +686,6 @@ int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned 
     c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = Oc + (long long)b * N * np4; c.ld_out = np4; c.out_batch = cs_o;
     AF2_TRY(launch_gemm(c, s));
   }
-  if (fused_front && g_fuse_tail)   // LN over channels * out_gate -> to_out -> + residual in one launch
-    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->w_ext_out, x, s);
   // LN over channels * out_gate -> token-major bf16
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
@@ -764,7 +741,7 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   if (fused_front) {
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = m; pc.T = Tm; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = m; pc.T = Tm; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = msa_mask; pc.nseg = 1;
     pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, cs_lr};
     AF2_TRY(launch_proj(pc, s));
@@ -784,8 +761,6 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
     g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)b * N * np4; g.ld_out = np4; g.out_batch = cs_o;
     AF2_TRY(launch_gemm(g, s));
   }
-  if (fused_front && g_fuse_tail)
-    return launch_tail(2, Oc, cs_o, Tx, d, nullptr, nullptr, nullptr, msa_mask ? scale : nullptr, 1.0f / (float)S, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = B * N; cp.n = N; cp.d = d; cp.mode = 1;
@@ -851,13 +826,12 @@ int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsi
   if (g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && pitch == inner) {
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = x; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = x; pc.T = tokens; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = mask; pc.nseg = 3;
     const int tl = (d + 127) / 128;
     pc.seg[0] = ProjOut{tl, EK_GATED_CH_SIG, d, Lc, chan_stride};
     pc.seg[1] = ProjOut{tl, EK_GATED_CH_SIG, d, Rc, chan_stride};
-    if (g_fuse_tail) pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_CH_SIG, d, gate, tokens};   // channel-major, consumed by af2_triangle_contract
-    else pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
+    pc.seg[2] = ProjOut{(d + 255) / 256, EK_STORE_TOK_SIG, d, gate, (long long)d};
     return launch_proj(pc, s);
   }
   LnParams lp;
@@ -928,8 +902,6 @@ int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc,
     }
     AF2_TRY(launch_gemm(c, s));
   }
-  if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && w->bn == 256 && proj_dim_ok(d) && cols % 8 == 0)   // same predicate as af2_triangle_project
-    return launch_tail(1, Oc, cs_o, T, d, w->on_gamma, w->on_beta, gate, nullptr, 0.f, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = cp4; cp.rows = rows; cp.n = cols; cp.d = d; cp.mode = 0;
@@ -963,7 +935,7 @@ int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned
   if (g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && pitch == inner) {
     ProjCall pc;
     memset(&pc, 0, sizeof(pc));
-    pc.a_mode = 0; pc.x = m; pc.T = tokens; pc.d = d; pc.gamma = w->ln_gamma; pc.beta = w->ln_beta;
+    pc.x = m; pc.T = tokens; pc.d = d;
     pc.w_cat = w->w_cat; pc.w_ext = w->w_ext; pc.rowmask = msa_mask; pc.nseg = 1;
     pc.seg[0] = ProjOut{(2 * d + 255) / 256, EK_STORE_CH, 2 * d, LRc, chan_stride};
     return launch_proj(pc, s);
@@ -1022,8 +994,6 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
     g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc + (long long)p * pc; g.ld_out = np4; g.out_batch = cs_o;
     AF2_TRY(launch_gemm(g, s));
   }
-  if (g_fuse_tail && g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && N % 4 == 0)
-    return launch_tail(2, Oc, cs_o, T, d, nullptr, nullptr, nullptr, msa_mask_full ? scale : nullptr, 1.0f / (float)S, w->w_out, w->w_ext_out, x, s);
   ChanLnParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.src = Oc; cp.chan_stride = cs_o; cp.pitch = np4; cp.rows = rows; cp.n = N; cp.d = d; cp.mode = 1;

@@ -1,13 +1,9 @@
-// Fused  [A-producer] -> multi-segment projection GEMM  for K = d <= 256 on tcgen05, CTA-pair (cta_group::2) MMA.
+// Fused  LayerNorm -> multi-segment projection GEMM  for K = d <= 256 on tcgen05, CTA-pair (cta_group::2) MMA.
 //
-//   out_seg = epilogue_seg( A[T, d] * Wcat[tiles of 256 rows, d]^T + bcat )        A produced IN the kernel:
-//     mode 0: A = (x - mean(x)) * rstd(x)               x fp32 token-major [T, d].  The LayerNorm affine is folded into
-//             the packed operands on the host (W' = W diag(gamma), b' = W beta + b), so this IS LayerNorm -> Linear
-//             (alphafold2.py:82-85, 210-217 + 114-118, 269-276 + 297-311, 330-340); optional pair-bias side output
-//             bias[h][pos(t)] = <x_raw[t], w_edge[h]>  (alphafold2.py:214-217, 245-247)
-//     mode 1: A = (LayerNorm_c(O[c][t]) * gamma + beta) * gate[c][t]   O fp32 channel-major, gate bf16 channel-major
-//             (triangle-multiply tail, alphafold2.py:315-316)
-//     mode 2: A = O[c][t] * scale[t]                                  (outer-mean tail, alphafold2.py:345-349)
+//   out_seg = epilogue_seg( LN(x)[T, d] * Wcat[tiles of 256 rows, d]^T + bcat )
+// x is the fp32 token-major residual stream; the LayerNorm affine is folded into the packed operands on the host
+// (W' = W diag(gamma), b' = W beta + b), so the kernel's producer computes (x - mean) * rstd only.  This is every
+// LN -> Linear cluster of the reference: alphafold2.py:82-85, 210-217 + 114-118, 269-276 + 297-311, 330-340.
 //
 // Why this shape: the K = 256 projections of the Evoformer are L2->SM bandwidth bound when tiled 128 x 256 with
 // both operands streamed (192 KB of operand per 16.8 MFLOP; the L2 caps near 6300 B/clk chip-wide).  Here
@@ -17,16 +13,16 @@
 //   * two CTAs of a cluster form a pair: one tcgen05.mma.cta_group::2 covers M = 256 rows (128 per CTA) x N = 256,
 //     each CTA stages only its half of the weight tile (TMA, 16 KB per k-block), halving weight traffic per FLOP;
 //   * one launch serves several outputs with different epilogue programs (q|k|v + gate; left + right + out-gate ...)
-//     so the normalised activations are never re-read.
-// The kernel is specialised at compile time on (pair / single CTA, producer mode, set of epilogue kinds) so each
-// instantiation carries only the code it runs (the all-in-one version was instruction-cache bound).
+//     so the normalised activations are never re-read;
+//   * the bias enters through the tensor core: every column tile starts with one extra K = 16 MMA step
+//     ones[128 x 16] x Bext[256 x 16]^T  (Bext columns 0 / 1 = bf16 hi / lo split of the fp32 bias), so the epilogue
+//     neither loads nor adds biases and hands the accumulator stage back as soon as its TMEM loads have landed.
+// The kernel is specialised at compile time on (pair / single CTA, set of epilogue kinds) so each instantiation carries
+// only the code it runs (the all-in-one version was instruction-cache bound).
 // Warp roles per CTA (512 threads): 0 weight-tile TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator |
-// 3 residual prefetch into the staging buffers (EK_RESID_F32 only) | 4..11 epilogue, two groups of four warps, each
-// group with its own 16 KB staging buffer (TMEM -> regs -> swizzled smem -> TMA store) | 12..15 A producers.
-// Accumulators are double buffered in TMEM (2 x 256 columns per CTA).  The bias enters through the tensor core: every
-// column tile starts with one extra K = 16 MMA step  ones[128 x 16] x Bext[256 x 16]^T  (Bext columns 0 / 1 = bf16 hi / lo
-// split of the fp32 bias), so the epilogue neither loads nor adds biases and can hand the accumulator stage back to the
-// MMA as soon as its TMEM loads have landed.
+// 3 idle | 4..11 epilogue: each warp autonomous (its 32 TMEM lanes, every second 32-column chunk, two private 2 KB
+// staging buffers, its own TMA stores; no block barriers) | 12..15 LayerNorm producers (8 lanes per row).
+// Accumulators are double buffered in TMEM (2 x 256 columns per CTA).
 #pragma once
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
@@ -44,7 +40,6 @@ constexpr int PK_TRI = KBIT(EK_GATED_CH_SIG) | KBIT(EK_STORE_TOK_SIG);    // lef
 constexpr int PK_TRI_CH = KBIT(EK_GATED_CH_SIG) | KBIT(EK_STORE_CH_SIG);  // ... with a channel-major out gate (fused tail)
 constexpr int PK_FF = KBIT(EK_GATED_TOK_GELU);                            // GEGLU
 constexpr int PK_OUTER = KBIT(EK_STORE_CH);                               // left | right (masked, channel-major)
-constexpr int PK_TAIL = KBIT(EK_RESID_F32);                               // output projection + residual
 
 struct ProjSeg {
   int tile0, ntiles;     // accumulator-column tiles (256 columns each) [tile0, tile0 + ntiles)
@@ -55,34 +50,17 @@ struct ProjSeg {
 };
 
 struct ProjParams {
-  // ---- A producer ----
-  const float* x;                // mode 0: [T, d] fp32;  mode 1/2: channel-major fp32, element (c, t) at c*src_cs + t
+  const float* x;                // [T, d] fp32 token-major residual stream
   long long T;
   int d;
   float inv_d;
-  long long src_cs;              // channel stride (modes 1/2)
-  const float* gamma;            // modes 1 only (mode 0: folded into the weights)
-  const float* beta;
   float eps;
-  const __nv_bfloat16* gate_cm;  // mode 1: bf16 channel-major gate, element (c, t) at c*gate_cs + t
-  long long gate_cs;
-  const float* scale;            // mode 2: [T] or nullptr -> scale_const
-  float scale_const;
-  // pair-bias side output (mode 0, PK_ATTN)
-  const float* wb;               // [H, d] fp32 or nullptr
-  __nv_bfloat16* bias_out;
-  int heads;
-  long long bias_hs;
-  int n_inner, pitch;
-  // ---- GEMM / epilogue ----
   const unsigned char* rowmask;  // [T] bool row scale or nullptr (kinds with rowscale)
   int nseg;
   ProjSeg seg[PROJ_MAX_SEG];
   int n_tiles_total;
   int nsplit;                    // column chunks per row unit
   int m_tiles;                   // ceil(T / 128)
-  int dbg;                       // bottleneck hunting (AF2_PROJ_DBG): 1 no staging/store, 2 no producer loads, 4 no math,
-                                 // 8 producer skips everything but the handshake, 16 epilogue releases without TMEM loads
 };
 
 template <int CTAS>
@@ -90,8 +68,8 @@ struct ProjSmem {
   static constexpr int STAGES = CTAS == 2 ? 4 : 1;      // (the single-CTA variant is a debugging aid only)
   static constexpr int B_ROWS = 256 / CTAS;
   static constexpr int B_STAGE = B_ROWS * GEMM_BK * 2;               // 16 KB (pair) / 32 KB
-  static constexpr int EPI_BUFS = 4;                                  // two 8 KB staging buffers per epilogue warp group
-  static constexpr int EPI_BYTES = 8192;                              // 128 rows x 64 B (32 bf16 / 16 fp32 columns)
+  static constexpr int EPI_BUFS = 16;                                 // two private staging buffers per epilogue warp
+  static constexpr int EPI_BYTES = 2048;                              // 32 rows x 64 B (32 bf16 columns)
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = 2 * PROJ_A_BUF;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE;
@@ -134,110 +112,60 @@ __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t*
   for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 
-// 32 packed output columns of this thread's row -> 8 KB staging buffer
-//   token layout  : [128 rows][64 B], 64B swizzle (TMA box 32 cols x 128 rows)
-//   channel layout: [32 channels][128 tokens] as two 64-token boxes of 32 rows x 128 B, 128B swizzle
-template <int LAYOUT>
-__device__ __forceinline__ void proj_stage32(uint8_t* eb, int row_in_tile, const uint32_t (&pk)[16]) {
-  if constexpr (LAYOUT == LAYOUT_TOKEN) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<uint4*>(eb + swz64_off(row_in_tile, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  } else {
-    uint8_t* bx = eb + (row_in_tile >> 6) * 4096;
-    const uint32_t tl = row_in_tile & 63;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t c0 = 2 * j, c1 = c0 + 1;
-      *reinterpret_cast<uint16_t*>(bx + c0 * 128 + ((((tl >> 3) ^ (c0 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] & 0xffffu);
-      *reinterpret_cast<uint16_t*>(bx + c1 * 128 + ((((tl >> 3) ^ (c1 & 7)) << 4) | ((tl & 7) << 1))) = static_cast<uint16_t>(pk[j] >> 16);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // epilogue of one 128 x 256 accumulator tile (one CTA's rows), kind fixed at compile time.
-// A chunk = 32 bf16 (16 fp32) output columns = one 8 KB staging buffer.  Chunk ec of the CTA goes to epilogue group
-// ec & 1; each group alternates between its own two buffers, so the TMA store of a chunk reads shared memory while the
-// next chunk is produced.  `release` is called by every warp right after the TMEM loads of its LAST chunk of the tile
-// have landed: the accumulator stage goes back to the MMA warp before the math / staging / store of that chunk.
+// Every epilogue warp is autonomous: it owns the 32 accumulator rows of its TMEM lane quarter, every second 32-column
+// chunk of them (the other chunks belong to the warp of the other group on the same quarter), two private 2 KB staging
+// buffers and its own TMA stores (box 32 columns x 32 rows) -- no block barriers anywhere in the epilogue.  The TMEM load
+// of the next chunk is in flight while the current one is converted, staged and stored.  `release` is called right
+// after the loads of the warp's LAST chunk of the tile have landed: the accumulator stage goes back to the MMA warp
+// before that chunk is converted.
 // ---------------------------------------------------------------------------------------------------
 template <int EK, class Release>
-__device__ __forceinline__ void proj_epilogue_tile(uint8_t* epi_base, uint64_t* efull_bar, uint64_t* eempty_bar, uint32_t& ec,
-                                                   uint32_t& gc, int grp, bool leader_thread, uint32_t t_acc,
-                                                   const CUtensorMap* tmc, float rs, int row_in_tile, int m0, int col0,
-                                                   int ncols, Release release, int dbg) {
+__device__ __forceinline__ void proj_epilogue_tile(uint8_t* wbuf, uint32_t& ec, uint32_t& gc, int grp, int lane, uint32_t t_acc,
+                                                   const CUtensorMap* tmc, float rs, int m0w, int col0, int ncols,
+                                                   Release release) {
   constexpr int mode = EpiTraits<EK>::mode, layout = EpiTraits<EK>::layout;
-  constexpr bool out_f32 = (mode == EPI_RESID_F32) || (mode == EPI_STORE_F32);
   constexpr bool gated = (mode == EPI_GATED_BF16);
-  constexpr int CW = out_f32 ? 16 : 32;
-  const int nchunks = (ncols + CW - 1) / CW;
-  // last chunk of this tile that belongs to this group (-1: none -> release immediately)
-  int last_cc = nchunks - 1;
-  if (last_cc >= 0 && ((ec + last_cc) & 1) != static_cast<uint32_t>(grp)) --last_cc;
-  if (dbg & 256) { if (last_cc >= 0) release(); last_cc = -2; }     // timing experiment: hand the stage back before draining it
-  if (last_cc == -1) release();
-  for (int cc = 0; cc < nchunks; ++cc, ++ec) {
-    if ((ec & 1) != static_cast<uint32_t>(grp)) continue;
-    if (dbg & 16) { if (cc == last_cc) release(); ++gc; continue; }
-    const int bufi = grp * 2 + static_cast<int>(gc & 1);
-    uint8_t* eb = epi_base + bufi * 8192;
-    if constexpr (out_f32) {
-      uint32_t u[16];
-      tmem_ld16(t_acc + cc * 16, u);
-      // reclaim the buffer (the store issued two chunks ago has read it); the residual tile is then prefetched into it
-      if (leader_thread) {
-        tma_store_wait_read<1>();
-        mbar_arrive(&eempty_bar[bufi]);
-      }
-      tmem_ld_wait();
-      if (cc == last_cc) release();
-      mbar_wait(&efull_bar[bufi], (gc >> 1) & 1);
+  const int nchunks = (ncols + 31) / 32;
+  const int first = ((ec & 1) == static_cast<uint32_t>(grp)) ? 0 : 1;     // this warp's chunks: first, first + 2, ...
+  ec += nchunks;
+  if (first >= nchunks) { release(); return; }
+  uint32_t u[32], g[gated ? 32 : 1];
+  tmem_ld32(t_acc + first * 32, u);
+  if constexpr (gated) tmem_ld32(t_acc + 128 + first * 32, g);
+  for (int cc = first; cc < nchunks; cc += 2) {
+    uint32_t pk[16];
+    tmem_ld_wait();
+    if (cc + 2 >= nchunks) release();
+    proj_finish32<EK>(u, g, rs, pk);
+    if (cc + 2 < nchunks) {                         // next chunk's loads overlap staging + store of this one
+      tmem_ld32(t_acc + (cc + 2) * 32, u);
+      if constexpr (gated) tmem_ld32(t_acc + 128 + (cc + 2) * 32, g);
+    }
+    uint8_t* eb = wbuf + (gc & 1) * 2048;
+    // the store that used this buffer two chunks ago must have read it (one newer store may still be in flight)
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    if constexpr (layout == LAYOUT_TOKEN) {
+      // [32 rows][64 B], 64B swizzle
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4* sp = reinterpret_cast<float4*>(eb + swz64_off(row_in_tile, j));
-        float4 o = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
-                               __uint_as_float(u[4 * j + 3]));
-        if constexpr (mode == EPI_RESID_F32) {
-          const float4 r4 = *sp;
-          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-        }
-        *sp = o;
-      }
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(eb + swz64_off(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     } else {
-      uint32_t pk[16];
-      {
-        uint32_t u[32];
-        tmem_ld32(t_acc + cc * 32, u);
-        if constexpr (gated) {
-          uint32_t g[32];
-          tmem_ld32(t_acc + 128 + cc * 32, g);
-          tmem_ld_wait();
-          if (cc == last_cc) release();
-          proj_finish32<EK>(u, g, rs, pk);
-        } else {
-          tmem_ld_wait();
-          if (cc == last_cc) release();
-          proj_finish32<EK>(u, nullptr, rs, pk);
-        }
+      // [32 channels][32 tokens x 2 B], 64B swizzle; lane = token
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t c0 = 2 * j, c1 = c0 + 1;
+        *reinterpret_cast<uint16_t*>(eb + c0 * 64 + ((((lane >> 3) ^ ((c0 >> 1) & 3)) << 4) | ((lane & 7) << 1))) = static_cast<uint16_t>(pk[j] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(eb + c1 * 64 + ((((lane >> 3) ^ ((c1 >> 1) & 3)) << 4) | ((lane & 7) << 1))) = static_cast<uint16_t>(pk[j] >> 16);
       }
-      if (dbg & 1) { if (pk[0] == 0x12345678u && pk[3] == 0x1u) release(); ++gc; continue; }
-      // the store that used this buffer two chunks ago must have read it (one newer store may still be in flight)
-      if (leader_thread) tma_store_wait_read<1>();
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-      proj_stage32<layout>(eb, row_in_tile, pk);
     }
     fence_proxy_async_smem();
-    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (leader_thread) {
-      if constexpr (layout == LAYOUT_TOKEN) {
-        tma_store_3d(tmc, eb, col0 + cc * CW, m0, 0);
-      } else {
-        tma_store_3d(tmc, eb, m0, col0 + cc * 32, 0);
-        tma_store_3d(tmc, eb + 4096, m0 + 64, col0 + cc * 32, 0);
-      }
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (layout == LAYOUT_TOKEN) tma_store_3d(tmc, eb, col0 + cc * 32, m0w, 0);
+      else tma_store_3d(tmc, eb, m0w, col0 + cc * 32, 0);
       tma_store_commit();
     }
     ++gc;
@@ -305,17 +233,13 @@ __device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abu
   }
 }
 
-template <int CTAS, int AMODE, int KINDS>
+template <int CTAS, int KINDS>
 __global__ void __launch_bounds__(PROJ_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC0,
                const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmX,
-               const __grid_constant__ ProjParams p) {
+               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ ProjParams p) {
   using L = ProjSmem<CTAS>;
   constexpr int STAGES = L::STAGES;
-  constexpr bool HAS_RESID = (KINDS & KBIT(EK_RESID_F32)) != 0;
-  constexpr bool HAS_BIAS = false;   // pair-bias side output of the producer: correct but slow (4 warps); the host uses the
-                                     // bias-only LayerNorm launch instead
   // 1024-byte aligned by declaration (128B-swizzle atoms); keeping the array symbol (no integer round-up of the pointer)
   // lets the compiler prove the shared address space and emit LDS/STS instead of generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -324,9 +248,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;                                // [STAGES] weight stage consumed
   uint64_t* tfull_bar = empty_bar + STAGES;                               // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                                   // [2] accumulator drained (leader's)
-  uint64_t* efull_bar = tempty_bar + 2;                                   // [4] residual tile landed in staging buffer
-  uint64_t* eempty_bar = efull_bar + 4;                                   // [4] staging buffer reclaimed
-  uint64_t* afull_bar = eempty_bar + 4;                                   // [2] A buffer produced (leader's)
+  uint64_t* afull_bar = tempty_bar + 2;                                   // [2] A buffer produced (leader's)
   uint64_t* aempty_bar = afull_bar + 2;                                   // [2] A buffer consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
@@ -353,10 +275,6 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       mbar_init(&tempty_bar[s], 8 * CTAS);
       mbar_init(&afull_bar[s], 4 * CTAS);
       mbar_init(&aempty_bar[s], 1);
-    }
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(&efull_bar[s], 1);
-      mbar_init(&eempty_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -482,47 +400,20 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 3) {
-    // ===================== residual prefetch into the epilogue groups' staging buffers ==================
-    if constexpr (HAS_RESID) {
-      if (lane == 0) {
-        uint32_t ec = 0, gcnt[2] = {0u, 0u};
-        for (int it = 0; it < my_items; ++it) {
-          const int unit = item_unit(it), ch = item_chunk(it);
-          const int m0 = (unit * CTAS + static_cast<int>(rank)) * 128;
-          for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt) {
-            const ProjSeg& sg = p.seg[seg_of(nt)];
-            const int col0 = (nt - sg.tile0) * 256;
-            const int ncols = min(256, sg.out_cols - col0);
-            const int nchunks = ncols > 0 ? (ncols + 15) / 16 : 0;
-            for (int cc = 0; cc < nchunks; ++cc, ++ec) {
-              const int g = ec & 1;
-              const uint32_t k = gcnt[g]++;
-              const int bufi = g * 2 + static_cast<int>(k & 1);
-              mbar_wait(&eempty_bar[bufi], (k >> 1) & 1);          // group g reclaimed this buffer for its k-th chunk
-              mbar_arrive_expect_tx(&efull_bar[bufi], L::EPI_BYTES);
-              tma_load_3d(smem + L::EPI_OFF + bufi * L::EPI_BYTES, &tmR, &efull_bar[bufi], col0 + cc * 16, m0, 0);
-            }
-          }
-        }
-      }
-    }
   } else if (warp >= 4 && warp < 12) {
     // ================================ epilogue ====================================
-    const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;
-    const int row_in_tile = q * 32 + lane;
-    const bool leader_thread = (threadIdx.x == 128 + grp * 128);
+    const int q = warp & 3;                   // TMEM lane quarter = rows 32q .. 32q+31 of the tile
+    const int grp = (warp - 4) >> 2;          // chunk parity this warp takes
     uint32_t tempty_remote[2];
     tempty_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
     tempty_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
-    uint8_t* epi_base = smem + L::EPI_OFF;
+    uint8_t* wbuf = smem + L::EPI_OFF + (warp - 4) * 4096;     // two private 2 KB staging buffers
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ec = 0, gc = 0, tcnt = 0;
     for (int it = 0; it < my_items; ++it) {
       const int unit = item_unit(it), ch = item_chunk(it);
-      const int m0 = (unit * CTAS + static_cast<int>(rank)) * 128;
-      const long long row = static_cast<long long>(m0) + row_in_tile;
+      const int m0w = (unit * CTAS + static_cast<int>(rank)) * 128 + q * 32;
+      const long long row = static_cast<long long>(m0w) + lane;
       float rs = 1.0f;
       if (p.rowmask && row < p.T) rs = p.rowmask[row] ? 1.0f : 0.0f;
       for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt, ++tcnt) {
@@ -547,8 +438,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 #define AF2_PROJ_CASE(EKV)                                                                                               \
   if constexpr ((KINDS & KBIT(EKV)) != 0) {                                                                              \
     if (sg.kind == EKV)                                                                                                  \
-      proj_epilogue_tile<EKV>(epi_base, efull_bar, eempty_bar, ec, gc, grp, leader_thread, t_acc, tmc, rs, row_in_tile,  \
-                              m0, col0, ncols > 0 ? ncols : 0, release, p.dbg);                                          \
+      proj_epilogue_tile<EKV>(wbuf, ec, gc, grp, lane, t_acc, tmc, rs, m0w, col0, ncols > 0 ? ncols : 0, release);       \
   }
         AF2_PROJ_CASE(EK_STORE_TOK)
         AF2_PROJ_CASE(EK_STORE_TOK_SIG)
@@ -556,35 +446,30 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         AF2_PROJ_CASE(EK_STORE_CH_SIG)
         AF2_PROJ_CASE(EK_GATED_TOK_GELU)
         AF2_PROJ_CASE(EK_GATED_CH_SIG)
-        AF2_PROJ_CASE(EK_RESID_F32)
 #undef AF2_PROJ_CASE
       }
     }
-    if (leader_thread) tma_store_wait_read<0>();
+    if (lane == 0) tma_store_wait_read<0>();
   } else if (warp >= 12) {
     // ================================ A producers ====================================
     const int pw = warp - 12;
     uint32_t afull_remote[2];
     afull_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[0]), 0) : 0u;
     afull_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[1]), 0) : 0u;
-    const int nchunk = p.d >> 2;                 // float4 chunks per row (<= 64)
     const int sub = lane & 7;                    // lane within its row group
     const int rg = lane >> 3;                    // row group 0..3 of the warp instruction
     const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32 <= 8)
     RowQuad qa, qb;
-    if constexpr (AMODE == 0) {
-      if (my_items > 0)
-        proj_load_quad(qa, p.x, static_cast<long long>(item_unit(0) * CTAS + static_cast<int>(rank)) * 128 + pw * 32 + rg, p.T, p.d, nj, sub);
-    }
+    if (my_items > 0)
+      proj_load_quad(qa, p.x, static_cast<long long>(item_unit(0) * CTAS + static_cast<int>(rank)) * 128 + pw * 32 + rg, p.T, p.d, nj, sub);
     for (int it = 0; it < my_items; ++it) {
-      const int unit = item_unit(it), ch = item_chunk(it);
+      const int unit = item_unit(it);
       const long long m0 = static_cast<long long>(unit * CTAS + static_cast<int>(rank)) * 128;
       const int ab = it & 1;
       uint8_t* abuf = smem + L::A_OFF + ab * PROJ_A_BUF;
       mbar_wait(&aempty_bar[ab], ((it >> 1) & 1) ^ 1);
-      if constexpr (AMODE == 0) {
+      {
         // ---- token-major LayerNorm core: 4 rows per warp instruction, 8 steps per item, next step's loads in flight ----
-        (void)ch;
         const int r0 = pw * 32 + rg;             // this lane's row inside the tile at step 0 (step s: + 4 s)
         const long long rbase = m0 + r0;
         long long next_base = -1;                // first step of the next item (cross-item prefetch)
@@ -599,61 +484,11 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         }
 #pragma unroll 1
         for (int st = 0; st < 8; st += 2) {
-          if (p.dbg & 8) break;
-          if (p.dbg & 2) {
-            proj_process_quad(qa, abuf, r0 + st * 4, true, p.inv_d, p.eps, nj, sub);
-            proj_process_quad(qa, abuf, r0 + (st + 1) * 4, true, p.inv_d, p.eps, nj, sub);
-            continue;
-          }
           proj_load_quad(qb, p.x, rbase + (st + 1) * 4, p.T, p.d, nj, sub);
           proj_process_quad(qa, abuf, r0 + st * 4, (rbase + st * 4) < p.T, p.inv_d, p.eps, nj, sub);
           if (st + 2 < 8) proj_load_quad(qa, p.x, rbase + (st + 2) * 4, p.T, p.d, nj, sub);
           else if (next_base >= 0) proj_load_quad(qa, p.x, next_base + rg, p.T, p.d, nj, sub);
           proj_process_quad(qb, abuf, r0 + (st + 1) * 4, (rbase + (st + 1) * 4) < p.T, p.inv_d, p.eps, nj, sub);
-        }
-      } else {
-        // ---- channel-major source: warp pw owns tokens pw*32 .. +31 (lane = token), loops over channels ----
-        const int r = pw * 32 + lane;
-        const long long tok = m0 + r;
-        const bool ok = tok < p.T;
-        const float* src = p.x + (ok ? tok : 0);
-        if constexpr (AMODE == 1) {
-          // shifted single-pass moments (shift = first channel) keep the variance free of cancellation
-          const float shift = ok ? __ldg(src) : 0.f;
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll 16
-          for (int c = 0; c < p.d; ++c) {
-            const float vv = ok ? __ldg(src + c * p.src_cs) - shift : 0.f;
-            s1 += vv;
-            s2 += vv * vv;
-          }
-          const float ms = s1 * p.inv_d;
-          const float mean = ms + shift;
-          const float var = fmaxf(s2 * p.inv_d - ms * ms, 0.f);
-          const float rstd = rsqrtf(var + p.eps);
-          const __nv_bfloat16* gsrc = p.gate_cm + (ok ? tok : 0);
-#pragma unroll 8
-          for (int c = 0; c < p.d; c += 2) {
-            float o0 = 0.f, o1 = 0.f;
-            if (ok) {
-              const float v0 = __ldg(src + c * p.src_cs), v1 = __ldg(src + (c + 1) * p.src_cs);
-              const float g0 = __bfloat162float(gsrc[c * p.gate_cs]), g1 = __bfloat162float(gsrc[(c + 1) * p.gate_cs]);
-              o0 = ((v0 - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c)) * g0;
-              o1 = ((v1 - mean) * rstd * __ldg(p.gamma + c + 1) + __ldg(p.beta + c + 1)) * g1;
-            }
-            *reinterpret_cast<uint32_t*>(abuf + (c >> 6) * 16384 + swz128_off(r, (c & 63) >> 3) + (c & 7) * 2) = pack_bf16x2(o0, o1);
-          }
-        } else {
-          const float sc = ok ? (p.scale ? __ldg(p.scale + tok) : p.scale_const) : 0.f;
-#pragma unroll 16
-          for (int c = 0; c < p.d; c += 2) {
-            float o0 = 0.f, o1 = 0.f;
-            if (ok) {
-              o0 = __ldg(src + c * p.src_cs) * sc;
-              o1 = __ldg(src + (c + 1) * p.src_cs) * sc;
-            }
-            *reinterpret_cast<uint32_t*>(abuf + (c >> 6) * 16384 + swz128_off(r, (c & 63) >> 3) + (c & 7) * 2) = pack_bf16x2(o0, o1);
-          }
         }
       }
       fence_proxy_async_smem();

@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for d in 0 256 264; do
-  AF2_PROJ_DBG=$d timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_dbg_$d.csv \
-     python tools/profile_block.py > /dev/null 2>&1; echo "dbg $d rc=$?"
-done
+AF2_PROJ_DBG=744 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:proj_tc -s 6 -c 1 \
+   -o gpurun_out/prof_proj_dbg744 -f python tools/profile_block.py > gpurun_out/ncu_proj_dbg.log 2>&1; echo "rc=$?"
