@@ -31,6 +31,8 @@ namespace af2 {
 
 constexpr int PROJ_THREADS = 512;
 constexpr int PROJ_MAX_SEG = 4;
+constexpr int PROJ_NPROD = 4;             // producer warps per CTA (12..15, one per SM sub-partition: adding warps 2 / 3 slowed the
+                                          // epilogue warps of their sub-partitions by more than it gained)
 constexpr int PROJ_A_BUF = 65536;          // 128 rows x 256 K bf16 (4 k-blocks of 16 KB)
 
 __host__ __device__ constexpr int KBIT(int ek) { return 1 << ek; }
@@ -190,29 +192,26 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
-__device__ __forceinline__ void proj_load_quad(RowQuad& b, const float* x, long long row, long long T, int d, int nj, int sub) {
-  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+template <int NJ>
+__device__ __forceinline__ void proj_load_quad(RowQuad& b, const float4* xr, bool live) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    b.v[j] = (row < T && j < nj) ? ldg_stream(xr + j * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NJ; ++j) b.v[j] = live ? ldg_stream(xr + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abuf, int r, bool live, float inv_d, float eps, int nj,
-                                                  int sub) {
+template <int NJ>
+__device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abuf, int r, bool live, float inv_d, float eps, int sub) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s += (b.v[j].x + b.v[j].y) + (b.v[j].z + b.v[j].w);
+  for (int j = 0; j < NJ; ++j) s += (b.v[j].x + b.v[j].y) + (b.v[j].z + b.v[j].w);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   const float mean = s * inv_d;
   float sq = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j < nj) {
-      const float a = b.v[j].x - mean, bb = b.v[j].y - mean, cc = b.v[j].z - mean, dd = b.v[j].w - mean;
-      sq += a * a + bb * bb + cc * cc + dd * dd;
-    }
+  for (int j = 0; j < NJ; ++j) {
+    const float a = b.v[j].x - mean, bb = b.v[j].y - mean, cc = b.v[j].z - mean, dd = b.v[j].w - mean;
+    sq += a * a + bb * bb + cc * cc + dd * dd;
   }
   sq += __shfl_xor_sync(0xffffffffu, sq, 1);
   sq += __shfl_xor_sync(0xffffffffu, sq, 2);
@@ -223,13 +222,68 @@ __device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abu
   uint8_t* rowp = abuf + r * 128;
   const uint32_t sw = static_cast<uint32_t>(r & 7);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j < nj) {
-      const uint32_t chunk = static_cast<uint32_t>(((j & 1) * 8 + sub) >> 1);
-      const uint2 o = make_uint2(pack_bf16x2(fmaf(b.v[j].x, rs, sh), fmaf(b.v[j].y, rs, sh)),
-                                 pack_bf16x2(fmaf(b.v[j].z, rs, sh), fmaf(b.v[j].w, rs, sh)));
-      *reinterpret_cast<uint2*>(rowp + (j >> 1) * 16384 + ((chunk ^ sw) << 4) + (sub & 1) * 8) = o;
+  for (int j = 0; j < NJ; ++j) {
+    const uint32_t chunk = static_cast<uint32_t>(((j & 1) * 8 + sub) >> 1);
+    const uint2 o = make_uint2(pack_bf16x2(fmaf(b.v[j].x, rs, sh), fmaf(b.v[j].y, rs, sh)),
+                               pack_bf16x2(fmaf(b.v[j].z, rs, sh), fmaf(b.v[j].w, rs, sh)));
+    *reinterpret_cast<uint2*>(rowp + (j >> 1) * 16384 + ((chunk ^ sw) << 4) + (sub & 1) * 8) = o;
+  }
+}
+
+// One producer warp's share of the A tiles: steps (4 rows each) pi, pi + NP, ... of every item of this CTA.
+//   item_row0(it) -> first row of the CTA's tile of item `it`;  wait_empty(it) / signal_full(it): A buffer hand-off
+template <int NJ, int NP, class ItemRow, class WaitEmpty, class SignalFull>
+__device__ __forceinline__ void proj_producer_loop(const float* x, long long T, int d, float inv_d, float eps, uint8_t* a_base,
+                                                   int my_items, int pi, int lane, ItemRow item_row0, WaitEmpty wait_empty,
+                                                   SignalFull signal_full) {
+  const int sub = lane & 7, rg = lane >> 3;
+  constexpr int STEPS = 32;                       // 128 rows / 4
+  auto row_ptr = [&](long long row) { return reinterpret_cast<const float4*>(x + row * d) + sub; };
+  RowQuad qa, qb;
+  if (my_items > 0) {
+    const long long row = item_row0(0) + pi * 4 + rg;
+    proj_load_quad<NJ>(qa, row_ptr(row), row < T);
+  }
+  for (int it = 0; it < my_items; ++it) {
+    const long long m0 = item_row0(it);
+    uint8_t* abuf = a_base + (it & 1) * PROJ_A_BUF;
+    wait_empty(it);
+    const long long m_next = (it + 1 < my_items) ? item_row0(it + 1) : -1;
+    if (m_next >= 0) {
+      // pull the next item's tile (128 rows) into L2: one 128-byte line per lane and round, shared by the NP producer warps
+      const char* nb = reinterpret_cast<const char*>(x + m_next * d);
+      const long long nrows = (m_next + 128 <= T) ? 128 : (T > m_next ? T - m_next : 0);
+      const long long nbytes = nrows * d * 4;
+      for (long long o = (pi * 32 + lane) * 128LL; o < nbytes; o += NP * 32 * 128LL)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
     }
+    // steps pi, pi + NP, ...: process qa while qb's loads are in flight and vice versa
+    int st = pi;
+#pragma unroll 1
+    while (st < STEPS) {
+      const int st1 = st + NP, st2 = st + 2 * NP;
+      {
+        long long row; bool any = true;
+        if (st1 < STEPS) row = m0 + st1 * 4 + rg;
+        else if (m_next >= 0) row = m_next + pi * 4 + rg;           // first step of the next item
+        else { row = 0; any = false; }
+        proj_load_quad<NJ>(qb, row_ptr(row), any && row < T);
+      }
+      proj_process_quad<NJ>(qa, abuf, st * 4 + rg, (m0 + st * 4 + rg) < T, inv_d, eps, sub);
+      if (st1 >= STEPS) { qa = qb; break; }
+      {
+        long long row; bool any = true;
+        if (st2 < STEPS) row = m0 + st2 * 4 + rg;
+        else if (m_next >= 0) row = m_next + pi * 4 + rg;
+        else { row = 0; any = false; }
+        proj_load_quad<NJ>(qa, row_ptr(row), any && row < T);
+      }
+      proj_process_quad<NJ>(qb, abuf, st1 * 4 + rg, (m0 + st1 * 4 + rg) < T, inv_d, eps, sub);
+      st = st2;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) signal_full(it);
   }
 }
 
@@ -273,7 +327,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8 * CTAS);
-      mbar_init(&afull_bar[s], 4 * CTAS);
+      mbar_init(&afull_bar[s], PROJ_NPROD * CTAS);
       mbar_init(&aempty_bar[s], 1);
     }
     fence_barrier_init();
@@ -451,53 +505,22 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     }
     if (lane == 0) tma_store_wait_read<0>();
   } else if (warp >= 12) {
-    // ================================ A producers ====================================
-    const int pw = warp - 12;
+    // ================================ LayerNorm producers (warps 12..15) ====================================
+    const int pi = warp - 12;
     uint32_t afull_remote[2];
     afull_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[0]), 0) : 0u;
     afull_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[1]), 0) : 0u;
-    const int sub = lane & 7;                    // lane within its row group
-    const int rg = lane >> 3;                    // row group 0..3 of the warp instruction
-    const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32 <= 8)
-    RowQuad qa, qb;
-    if (my_items > 0)
-      proj_load_quad(qa, p.x, static_cast<long long>(item_unit(0) * CTAS + static_cast<int>(rank)) * 128 + pw * 32 + rg, p.T, p.d, nj, sub);
-    for (int it = 0; it < my_items; ++it) {
-      const int unit = item_unit(it);
-      const long long m0 = static_cast<long long>(unit * CTAS + static_cast<int>(rank)) * 128;
-      const int ab = it & 1;
-      uint8_t* abuf = smem + L::A_OFF + ab * PROJ_A_BUF;
-      mbar_wait(&aempty_bar[ab], ((it >> 1) & 1) ^ 1);
-      {
-        // ---- token-major LayerNorm core: 4 rows per warp instruction, 8 steps per item, next step's loads in flight ----
-        const int r0 = pw * 32 + rg;             // this lane's row inside the tile at step 0 (step s: + 4 s)
-        const long long rbase = m0 + r0;
-        long long next_base = -1;                // first step of the next item (cross-item prefetch)
-        if (it + 1 < my_items) {
-          next_base = static_cast<long long>(item_unit(it + 1) * CTAS + static_cast<int>(rank)) * 128 + pw * 32;
-          // pull the next item's 32 rows of this warp into L2 now (one 128 B line per lane and step); the register
-          // prefetch below then only has to cover L2 latency
-          const char* nb = reinterpret_cast<const char*>(p.x + next_base * p.d);
-          const long long nbytes = (next_base + 32 <= p.T ? 32LL : (p.T > next_base ? p.T - next_base : 0LL)) * p.d * 4;
-          for (long long o = lane * 128LL; o < nbytes; o += 32 * 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
-        }
-#pragma unroll 1
-        for (int st = 0; st < 8; st += 2) {
-          proj_load_quad(qb, p.x, rbase + (st + 1) * 4, p.T, p.d, nj, sub);
-          proj_process_quad(qa, abuf, r0 + st * 4, (rbase + st * 4) < p.T, p.inv_d, p.eps, nj, sub);
-          if (st + 2 < 8) proj_load_quad(qa, p.x, rbase + (st + 2) * 4, p.T, p.d, nj, sub);
-          else if (next_base >= 0) proj_load_quad(qa, p.x, next_base + rg, p.T, p.d, nj, sub);
-          proj_process_quad(qb, abuf, r0 + (st + 1) * 4, (rbase + (st + 1) * 4) < p.T, p.inv_d, p.eps, nj, sub);
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTAS == 2) mbar_arrive_cluster(afull_remote[ab]);
-        else mbar_arrive(&afull_bar[ab]);
-      }
-    }
+    auto item_row0 = [&](int it) { return static_cast<long long>(item_unit(it) * CTAS + static_cast<int>(rank)) * 128; };
+    auto wait_empty = [&](int it) { mbar_wait(&aempty_bar[it & 1], ((it >> 1) & 1) ^ 1); };
+    auto signal_full = [&](int it) {
+      if constexpr (CTAS == 2) mbar_arrive_cluster(afull_remote[it & 1]);
+      else mbar_arrive(&afull_bar[it & 1]);
+    };
+    uint8_t* a_base = smem + L::A_OFF;
+    const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32)
+    if (nj == 8) proj_producer_loop<8, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
+    else if (nj == 4) proj_producer_loop<4, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
+    else proj_producer_loop<6, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
   }
 
   __syncwarp();
