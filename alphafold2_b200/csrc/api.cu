@@ -304,17 +304,30 @@ int launch_layernorm(const LnParams& p, cudaStream_t s) {
 }
 
 // pair bias <x_raw, w_edge> of T tokens (d % 32 == 0, d <= 256, heads <= 8), else the LayerNorm kernel's bias path
-bool pair_bias_fast_ok(int d, int heads) { return d % 32 == 0 && d <= 256 && heads <= 8; }
+bool pair_bias_fast_ok(int d, int heads) { return d % 32 == 0 && d >= 32 && d <= 256 && heads <= 8; }
 int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_bfloat16* bias_out, int heads, long long bias_hs,
                      int n_inner, int pitch, cudaStream_t s) {
   if (T <= 0) return AF2_OK;
   PairBiasParams p;
   p.x = x; p.T = T; p.d = d; p.wb = wb; p.bias_out = bias_out; p.heads = heads; p.bias_hs = bias_hs; p.n_inner = n_inner; p.pitch = pitch;
-  const long long need = (T + 31) / 32;                // 8 warps x 4 tokens per block iteration
-  const long long cap = (long long)sm_count() * 8;
+  if (T > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "pair_bias: too many tokens");
+  const bool mma = (d == 256 || d == 128);
+  const long long need = mma ? (T + 127) / 128 : (T + 31) / 32;   // 8 warps x 16 (tensor-core kernel) / 4 tokens per block iteration
+  const long long cap = (long long)sm_count() * 3;     // persistent: 3 resident blocks per SM
   const int grid = (int)(need < cap ? need : cap);
   ProfScope ps(s, KC_LAYERNORM, 0.0, (double)T * d * 4 + (double)T * heads * 2);
-  pair_bias_kernel<<<grid, 256, (size_t)heads * d * sizeof(float), s>>>(p);
+  if (mma && d == 256) pair_bias_mma_kernel<16><<<grid, 256, 0, s>>>(p);
+  else if (mma) pair_bias_mma_kernel<8><<<grid, 256, 0, s>>>(p);
+  else {
+    switch (d / 32) {
+      case 7: pair_bias_kernel<7><<<grid, 256, 0, s>>>(p); break;
+      case 6: pair_bias_kernel<6><<<grid, 256, 0, s>>>(p); break;
+      case 5: pair_bias_kernel<5><<<grid, 256, 0, s>>>(p); break;
+      case 3: pair_bias_kernel<3><<<grid, 256, 0, s>>>(p); break;
+      case 2: pair_bias_kernel<2><<<grid, 256, 0, s>>>(p); break;
+      default: pair_bias_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    }
+  }
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }
@@ -324,13 +337,20 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
   if (p.pitch == p.n && p.d % 64 == 0 && p.d <= 256 && (T % 4) == 0) {
     // dense token grid: 64-token tiles, fully coalesced
     const size_t smem = (size_t)p.d * 64 * sizeof(float) + 8 * 64 * 2 * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 64 * 4 + 4096));
+      CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 64 * 4 + 4096));
+      configured = true;
     }
     ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)T * p.d * (p.mode == 0 ? 8.0 : 6.0));
-    chan_to_token_tile_kernel<<<(unsigned)((T + 63) / 64), 512, smem, s>>>(p, T);
+    const unsigned grid = (unsigned)((T + 63) / 64);
+    switch (p.d / 64) {
+      case 4: chan_to_token_tile_kernel<32><<<grid, 512, smem, s>>>(p, T); break;
+      case 3: chan_to_token_tile_kernel<24><<<grid, 512, smem, s>>>(p, T); break;
+      case 2: chan_to_token_tile_kernel<16><<<grid, 512, smem, s>>>(p, T); break;
+      default: chan_to_token_tile_kernel<8><<<grid, 512, smem, s>>>(p, T); break;
+    }
     CUDA_OK(cudaGetLastError());
     return AF2_OK;
   }

@@ -200,33 +200,37 @@ struct PairBiasParams {
   int n_inner, pitch;
 };
 
-__global__ void __launch_bounds__(256) pair_bias_kernel(const PairBiasParams p) {
-  extern __shared__ float wsm[];                       // [heads][d]
-  for (int i = threadIdx.x; i < p.heads * p.d; i += blockDim.x) wsm[i] = __ldg(p.wb + i);
-  __syncthreads();
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256, 3) pair_bias_kernel(const PairBiasParams p) {
+  // No shared-memory prologue: w_edge (<= 8 KB) is read through L1 (every lane group reads the same 128 bytes), the
+  // activations stream past L1 (no_allocate), so a block starts loading tokens immediately.
   const int lane = threadIdx.x & 31, sub = lane & 7, rg = lane >> 3;
-  const int nj = p.d >> 5;                             // float4 chunks per lane
-  const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long t0 = warp_global * 4; t0 < p.T; t0 += nwarps * 4) {
-    const long long t = t0 + rg;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int groups = static_cast<int>((p.T + 3) / 4);
+  for (int gidx = warp_global; gidx < groups; gidx += nwarps) {
+    const long long t = static_cast<long long>(gidx) * 4 + rg;
     const bool live = t < p.T;
-    float4 v[8];
-    const float4* xr = reinterpret_cast<const float4*>(p.x + (live ? t : 0) * p.d);
+    float4 v[NJ];
+    const float4* xr = reinterpret_cast<const float4*>(p.x + (live ? t : 0) * p.d) + sub;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (live && j < nj) ? __ldg(xr + j * 8 + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NJ; ++j) v[j] = live ? ldg_stream4(xr + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
     float acc[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       acc[h] = 0.f;
       if (h < p.heads) {
-        const float4* wr = reinterpret_cast<const float4*>(wsm + h * p.d);
+        const float4* wr = reinterpret_cast<const float4*>(p.wb + h * p.d) + sub;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nj) {
-            const float4 w = wr[j * 8 + sub];
-            acc[h] += v[j].x * w.x + v[j].y * w.y + v[j].z * w.z + v[j].w * w.w;
-          }
+        for (int j = 0; j < NJ; ++j) {
+          const float4 w = __ldg(wr + j * 8);
+          acc[h] += v[j].x * w.x + v[j].y * w.y + v[j].z * w.z + v[j].w * w.w;
         }
       }
     }
@@ -246,10 +250,81 @@ __global__ void __launch_bounds__(256) pair_bias_kernel(const PairBiasParams p) 
     }
     const bool hi1 = sub & 1;
     const float res = (hi1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, hi1 ? r2[0] : r2[1], 1);
-    // lane sub now holds head index: bit2 = sub&4 -> +4, bit1 -> +2, bit0 -> +1  == sub
     if (live && sub < p.heads) {
-      const long long off = (t / p.n_inner) * p.pitch + (t % p.n_inner);
+      const int ti = static_cast<int>(t);                        // T < 2^31 (checked by the host)
+      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
       p.bias_out[sub * p.bias_hs + off] = __float2bfloat16(res);
+    }
+  }
+}
+
+// Tensor-core variant (legacy mma.sync m16n8k16, N = 8 heads is exactly one MMA tile): the SIMT kernel above is bound by
+// the load-instruction rate of w_edge (64 loads per 4 tokens); here w_edge lives in B fragments (registers) for the whole
+// kernel and x streams through A fragments.  Both operands are split hi + lo into bf16 fragments and three products
+// (hi*hi + lo*hi + hi*lo) are accumulated in fp32, i.e. ~16 mantissa bits per operand: the bias matches the fp32 dot
+// product of the reference to ~1e-5 relative before its bf16 store.
+template <int KSTEPS>   // d / 16
+__global__ void __launch_bounds__(256, 2) pair_bias_mma_kernel(const PairBiasParams p) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  // B fragments: B[k][n] = w_edge[n][k]; thread holds k = 16 ks + {2t, 2t+1} and {2t+8, 2t+9} of head n = g
+  uint32_t bfrag[KSTEPS][2], blo[KSTEPS][2];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
+    if (g < p.heads) {
+      w0 = __ldg(reinterpret_cast<const float2*>(p.wb + g * p.d + ks * 16 + 2 * t));
+      w1 = __ldg(reinterpret_cast<const float2*>(p.wb + g * p.d + ks * 16 + 2 * t + 8));
+    }
+    bfrag[ks][0] = pack_bf16x2(w0.x, w0.y);
+    bfrag[ks][1] = pack_bf16x2(w1.x, w1.y);
+    blo[ks][0] = pack_bf16x2(w0.x - bf16lo_to_f32(bfrag[ks][0]), w0.y - bf16hi_to_f32(bfrag[ks][0]));
+    blo[ks][1] = pack_bf16x2(w1.x - bf16lo_to_f32(bfrag[ks][1]), w1.y - bf16hi_to_f32(bfrag[ks][1]));
+  }
+  const int groups = static_cast<int>((p.T + 15) / 16);
+  for (int gi = warp_global; gi < groups; gi += nwarps) {
+    const long long r0 = static_cast<long long>(gi) * 16 + g, r1 = r0 + 8;
+    const bool l0 = r0 < p.T, l1 = r1 < p.T;
+    const float* x0 = p.x + (l0 ? r0 : 0) * p.d + 2 * t;
+    const float* x1 = p.x + (l1 ? r1 : 0) * p.d + 2 * t;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      float2 a[4];
+      a[0] = l0 ? __ldg(reinterpret_cast<const float2*>(x0 + ks * 16)) : make_float2(0.f, 0.f);
+      a[1] = l1 ? __ldg(reinterpret_cast<const float2*>(x1 + ks * 16)) : make_float2(0.f, 0.f);
+      a[2] = l0 ? __ldg(reinterpret_cast<const float2*>(x0 + ks * 16 + 8)) : make_float2(0.f, 0.f);
+      a[3] = l1 ? __ldg(reinterpret_cast<const float2*>(x1 + ks * 16 + 8)) : make_float2(0.f, 0.f);
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = pack_bf16x2(a[i].x, a[i].y);
+        lo[i] = pack_bf16x2(a[i].x - bf16lo_to_f32(hi[i]), a[i].y - bf16hi_to_f32(hi[i]));
+      }
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                   : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                   : "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(bfrag[ks][0]), "r"(bfrag[ks][1]));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                   : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                   : "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(bfrag[ks][0]), "r"(bfrag[ks][1]));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                   : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                   : "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(blo[ks][0]), "r"(blo[ks][1]));
+    }
+    // c0, c1: token r0, heads 2t, 2t+1;  c2, c3: token r1
+    const int h0 = 2 * t;
+    if (l0) {
+      const int ti = static_cast<int>(r0);
+      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
+      if (h0 < p.heads) p.bias_out[h0 * p.bias_hs + off] = __float2bfloat16(c[0]);
+      if (h0 + 1 < p.heads) p.bias_out[(h0 + 1) * p.bias_hs + off] = __float2bfloat16(c[1]);
+    }
+    if (l1) {
+      const int ti = static_cast<int>(r1);
+      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
+      if (h0 < p.heads) p.bias_out[h0 * p.bias_hs + off] = __float2bfloat16(c[2]);
+      if (h0 + 1 < p.heads) p.bias_out[(h0 + 1) * p.bias_hs + off] = __float2bfloat16(c[3]);
     }
   }
 }
@@ -260,39 +335,51 @@ __global__ void __launch_bounds__(256) pair_bias_kernel(const PairBiasParams p) 
 //   phase 1: 256-byte coalesced row segments src[c][t0 .. t0+63] -> shared tile [d][64] (16 independent 16-byte loads per thread)
 //   phase 2: thread = (token, 32-channel slice): LayerNorm over channels (mode 0) or scale (mode 1), gate, 64-byte bf16 stores
 // ------------------------------------------------------------------------------------------------
+template <int CPT>   // channels per thread = d / 8
 __global__ void __launch_bounds__(512) chan_to_token_tile_kernel(const ChanLnParams p, long long T) {
   extern __shared__ float tile[];                      // [d][64] followed by [8][64][2] partial moments
+  constexpr int D = CPT * 8;
   const long long t0 = static_cast<long long>(blockIdx.x) * 64;
   const int tid = threadIdx.x;
-  // ---- phase 1 ----
+  // ---- phase 1: D / 32 independent 16-byte loads per thread ----
   {
     const int q = tid & 15;                            // float4 index inside the 64-token segment
     const bool ok = (t0 + q * 4) < T;                  // T % 4 == 0 (pitch multiple of 4)
-    for (int c = tid >> 4; c < p.d; c += 32) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) v = __ldg(reinterpret_cast<const float4*>(p.src + static_cast<long long>(c) * p.chan_stride + t0) + q);
-      reinterpret_cast<float4*>(tile + c * 64)[q] = v;
+    const float4* src = reinterpret_cast<const float4*>(p.src + t0) + q;
+    float4 v[D / 32];
+#pragma unroll
+    for (int k = 0; k < D / 32; ++k) {
+      const int c = (tid >> 4) + k * 32;
+      v[k] = ok ? ldg_stream4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + static_cast<long long>(c) * p.chan_stride))
+                : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int k = 0; k < D / 32; ++k) reinterpret_cast<float4*>(tile + ((tid >> 4) + k * 32) * 64)[q] = v[k];
   }
   __syncthreads();
-  // ---- phase 2 ----
-  const int tok = tid & 63, slice = tid >> 6;          // 8 slices of d/8 channels
-  const int cpt = p.d >> 3;                            // channels per thread (<= 32)
+  // ---- phase 2: thread = (token, slice of CPT channels); the slice lives in registers ----
+  const int tok = tid & 63, slice = tid >> 6;
+  const int c0 = slice * CPT;
   const long long token = t0 + tok;
-  float* part = tile + p.d * 64;
+  float* part = tile + D * 64;
+  float x[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) x[i] = tile[(c0 + i) * 64 + tok];
   float mean = 0.f, rstd = 1.f;
   if (p.mode == 0) {
     float s1 = 0.f;
-    for (int i = 0; i < cpt; ++i) s1 += tile[(slice * cpt + i) * 64 + tok];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) s1 += x[i];
     part[(slice * 64 + tok) * 2] = s1;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += part[(k * 64 + tok) * 2];
-    mean = tot / p.d;
+    mean = tot * (1.0f / D);
     float s2 = 0.f;
-    for (int i = 0; i < cpt; ++i) {
-      const float a = tile[(slice * cpt + i) * 64 + tok] - mean;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const float a = x[i] - mean;
       s2 += a * a;
     }
     part[(slice * 64 + tok) * 2 + 1] = s2;
@@ -300,27 +387,30 @@ __global__ void __launch_bounds__(512) chan_to_token_tile_kernel(const ChanLnPar
     float var = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) var += part[(k * 64 + tok) * 2 + 1];
-    rstd = rsqrtf(var / p.d + p.eps);
+    rstd = rsqrtf(var * (1.0f / D) + p.eps);
   }
   if (token < T) {
-    const int c0 = slice * cpt;
     const float sc = (p.mode == 1) ? (p.scale ? __ldg(p.scale + token) : p.scale_const) : 1.f;
-    for (int i = 0; i < cpt; i += 8) {
+#pragma unroll
+    for (int i = 0; i < CPT; i += 8) {
       float o[8];
       if (p.mode == 0) {
-        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(p.gate + token * p.d + c0 + i));
+        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(p.gate + token * D + c0 + i));
         const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + i)), gb = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + i + 4));
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + i)), bb = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + i + 4));
+        const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int c = c0 + i + k;
           const float g = (k & 1) ? bf16hi_to_f32(gw[k >> 1]) : bf16lo_to_f32(gw[k >> 1]);
-          o[k] = ((tile[c * 64 + tok] - mean) * rstd * __ldg(p.gamma + c) + __ldg(p.beta + c)) * g;
+          o[k] = ((x[i + k] - mean) * rstd * gm[k] + bt[k]) * g;
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = tile[(c0 + i + k) * 64 + tok] * sc;
+        for (int k = 0; k < 8; ++k) o[k] = x[i + k] * sc;
       }
-      *reinterpret_cast<uint4*>(p.y + token * p.d + c0 + i) =
+      *reinterpret_cast<uint4*>(p.y + token * D + c0 + i) =
           make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
   }

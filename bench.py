@@ -286,16 +286,30 @@ def run_ours(args, rank, world, local_rank):
     peaks = measured_peaks()
     tot_ms = sum(c["ms"] for c in classes) or 1.0
     dom = max(classes, key=lambda c: c["ms"])
+    # DRAM traffic per launch of the dominant class from the committed `ncu --set full` capture of one C2 block
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+        if cand:
+            tj = json.load(open(cand[-1]))
+            if dom["name"] in tj:
+                traffic = tj[dom["name"]]["dram_bytes_per_launch"]
+                traffic_src = os.path.relpath(cand[-1], ROOT)
+    except Exception:
+        pass
     if dom["flops"] > 0:
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "frac": ach / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["launches"], 1),
+                "peak_source": peaks["source"] + ", sustained bf16",
                 "share_of_step": dom["ms"] / tot_ms, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
                 "flops_per_launch": dom["flops"] / max(dom["launches"], 1)}
     else:
         ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
                 "share_of_step": dom["ms"] / tot_ms, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1)}
     step_flops = flops_per_block(N_RES, N_SEQ, CFG["dim"], CFG["heads"], CFG["dim_head"]) * CFG["depth"]
     step_tf = step_flops / (ms_step * 1e-3) / 1e12
