@@ -220,13 +220,16 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
     if (c.cm_pitch != c.cm_inner || (c.ld_out * 2) % 16 != 0 || c.batch != 1 || out_f32) direct = true;
   }
   if (c.mode == EPI_RESID_F32 && ((c.ld_resid * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(c.resid) & 15) != 0)) direct = true;
+  // warp-autonomous residual epilogue: one column tile, one batch, whole accumulator tile valid
+  const bool resid_w = !direct && c.mode == EPI_RESID_F32 && BN == 256 && !c.mn_major && c.batch == 1 && c.N <= 256 &&
+                       p.out_cols == 256;
   CUtensorMap tc = ta, tr = ta;
   if (!direct) {
     const CUtensorMapDataType dt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (c.layout == LAYOUT_TOKEN) {
       unsigned long long dc[3] = {(unsigned long long)p.out_cols, (unsigned long long)c.M, (unsigned long long)c.batch};
       unsigned long long sc[2] = {(unsigned long long)c.ld_out * es, (unsigned long long)(c.batch > 1 ? c.out_batch : c.ld_out * c.M) * es};
-      unsigned bc[3] = {(unsigned)(out_f32 ? 32 : 64), 128, 1};
+      unsigned bc[3] = {(unsigned)(out_f32 ? 32 : 64), (unsigned)(resid_w ? 32 : 128), 1};
       AF2_TRY(make_tmap(&tc, c.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B, dt));
       if (c.mode == EPI_RESID_F32) {
         unsigned long long sr[2] = {(unsigned long long)c.ld_resid * 4, (unsigned long long)c.ld_resid * c.M * 4};
@@ -248,7 +251,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
     else if (c.mode == EPI_STORE_BF16 && c.layout == LAYOUT_CHANNEL && c.act == ACT_NONE) ek = EK_STORE_CH;
     else if (c.mode == EPI_GATED_BF16 && c.layout == LAYOUT_TOKEN && c.act == ACT_GELU && !c.use_rowscale) ek = EK_GATED_TOK_GELU;
     else if (c.mode == EPI_GATED_BF16 && c.layout == LAYOUT_CHANNEL && c.act == ACT_SIGMOID) ek = EK_GATED_CH_SIG;
-    else if (c.mode == EPI_RESID_F32) ek = EK_RESID_F32;
+    else if (c.mode == EPI_RESID_F32) ek = resid_w ? EK_RESID_F32_W : EK_RESID_F32;
     else if (c.mode == EPI_STORE_F32) ek = EK_STORE_F32;
   }
   if (c.mn_major) {
@@ -267,6 +270,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
       case EK_GATED_TOK_GELU: return launch_gemm_inst<256, 3, false, EK_GATED_TOK_GELU>(ta, tb, tc, tr, p, s);
       case EK_GATED_CH_SIG: return launch_gemm_inst<256, 3, false, EK_GATED_CH_SIG>(ta, tb, tc, tr, p, s);
       case EK_RESID_F32: return launch_gemm_inst<256, 3, false, EK_RESID_F32>(ta, tb, tc, tr, p, s);
+      case EK_RESID_F32_W: return launch_gemm_inst<256, 3, false, EK_RESID_F32_W>(ta, tb, tc, tr, p, s);
       case EK_STORE_F32: return launch_gemm_inst<256, 3, false, EK_STORE_F32>(ta, tb, tc, tr, p, s);
       default: return launch_gemm_inst<256, 3, false, EK_GENERIC>(ta, tb, tc, tr, p, s);
     }

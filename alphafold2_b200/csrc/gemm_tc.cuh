@@ -95,7 +95,8 @@ enum EpiKind : int {
   EK_GATED_CH_SIG = 5,    // bf16 channel-major, (u + b) * sigmoid(g + b) * rowscale (triangle left / right)
   EK_RESID_F32 = 6,       // fp32 token-major, acc + bias + residual                (every output projection)
   EK_STORE_F32 = 7,       // fp32 token-major                                       (per-channel contractions)
-  EK_STORE_CH_SIG = 8     // bf16 channel-major, sigmoid(acc + bias)                (triangle out_gate for the fused tail)
+  EK_STORE_CH_SIG = 8,    // bf16 channel-major, sigmoid(acc + bias)                (triangle out_gate for the fused tail)
+  EK_RESID_F32_W = 9      // EK_RESID_F32 with warp-autonomous epilogue warps (no block barriers; see the kernel)
 };
 template <int EK> struct EpiTraits { static constexpr int mode = -1, act = -1, layout = -1; static constexpr bool rowscale = true; };
 template <> struct EpiTraits<EK_STORE_TOK> { static constexpr int mode = EPI_STORE_BF16, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
@@ -104,6 +105,7 @@ template <> struct EpiTraits<EK_STORE_CH> { static constexpr int mode = EPI_STOR
 template <> struct EpiTraits<EK_GATED_TOK_GELU> { static constexpr int mode = EPI_GATED_BF16, act = ACT_GELU, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
 template <> struct EpiTraits<EK_GATED_CH_SIG> { static constexpr int mode = EPI_GATED_BF16, act = ACT_SIGMOID, layout = LAYOUT_CHANNEL; static constexpr bool rowscale = true; };
 template <> struct EpiTraits<EK_RESID_F32> { static constexpr int mode = EPI_RESID_F32, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
+template <> struct EpiTraits<EK_RESID_F32_W> { static constexpr int mode = EPI_RESID_F32, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
 template <> struct EpiTraits<EK_STORE_CH_SIG> { static constexpr int mode = EPI_STORE_BF16, act = ACT_SIGMOID, layout = LAYOUT_CHANNEL; static constexpr bool rowscale = false; };
 template <> struct EpiTraits<EK_STORE_F32> { static constexpr int mode = EPI_STORE_F32, act = ACT_NONE, layout = LAYOUT_TOKEN; static constexpr bool rowscale = false; };
 
@@ -170,6 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* efull_bar = tempty_bar + 2;         // [EPI_BUFS] staging buffer free (+ residual landed)
   uint64_t* eempty_bar = efull_bar + EPI_BUFS;  // [EPI_BUFS] staging buffer released by its TMA store
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty_bar + EPI_BUFS);
+  uint64_t* wres_bar = eempty_bar + EPI_BUFS + 1;   // [8 warps][2] residual box landed (EK_RESID_F32_W)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&efull_bar[s], 1);
       mbar_init(&eempty_bar[s], 1);
     }
+    for (int s = 0; s < 16; ++s) mbar_init(&wres_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -285,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 3) {
     // ===================== staging-buffer producer (residual prefetch) ==================
-    if (lane == 0 && !p.direct) {
+    if (lane == 0 && !p.direct && EK != EK_RESID_F32_W) {
       uint32_t ec = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_tiles;
@@ -306,6 +310,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (warp >= 4 && EK == EK_RESID_F32_W) {
+    // ============ epilogue, warp-autonomous (out = acc + bias + residual, fp32, BN = 256, TMA-describable) ============
+    // Every warp owns the 32 accumulator rows of its TMEM lane quarter and every second 32-column chunk of them, two
+    // private 4 KB staging buffers ([32 rows][128 B], 128B swizzle), prefetches its own residual boxes with TMA one
+    // chunk ahead (across tiles), adds in place and stores with its own TMA store: no block barriers, no helper warp.
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    uint8_t* wbuf = smem + L::EPI_OFF + (warp - 4) * 8192;
+    uint64_t* rbar = wres_bar + (warp - 4) * 2;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const NTile tl = p.tile;
+    const int my_tiles = (total_tiles > static_cast<int>(blockIdx.x)) ? (total_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    constexpr int CPW = 4;                                   // chunks per warp and tile (256 columns / 32 / 2 warps)
+    const int total_chunks = my_tiles * CPW;
+    auto chunk_coords = [&](int k, int& m0w, int& colc) {    // k-th chunk of this warp's stream
+      const int tile = blockIdx.x + (k / CPW) * gridDim.x;
+      const int mt = (tile / n_tiles) % m_tiles;             // (batch = 1, one column tile: EK_RESID_F32_W launches only)
+      m0w = mt * GEMM_BM + q * 32;
+      colc = (grp + 2 * (k % CPW)) * 32;
+    };
+    auto prefetch = [&](int k) {                             // lane 0: residual box of chunk k -> buffer k & 1
+      int m0w, colc;
+      chunk_coords(k, m0w, colc);
+      tma_store_wait_read<0>();                              // the store that used this buffer (chunk k - 2) has read it
+      mbar_arrive_expect_tx(&rbar[k & 1], 4096);
+      tma_load_3d(wbuf + (k & 1) * 4096, &tmR, &rbar[k & 1], colc, m0w, 0);
+    };
+    if (lane == 0 && total_chunks > 0) prefetch(0);
+    for (int k = 0; k < total_chunks; ++k) {
+      const int ti = k / CPW, ci = k % CPW;
+      const int acc = ti & 1;
+      int m0w, colc;
+      chunk_coords(k, m0w, colc);
+      if (ci == 0) {
+        mbar_wait(&tfull_bar[acc], (ti >> 1) & 1);
+        tc_fence_after();
+      }
+      uint32_t u[32];
+      tmem_ld32(tmem_base + acc * BN + lane_sel + colc, u);
+      float bv[32];
+      load_bias32(tl.bias ? tl.bias + colc : nullptr, bv);
+      // residual box of the next chunk into the other buffer: its last user, the store of chunk k - 1, was issued a whole
+      // chunk ago, so waiting for its smem read here is normally free
+      if (lane == 0 && k + 1 < total_chunks) prefetch(k + 1);
+      tmem_ld_wait();
+      if (ci == CPW - 1) {                                   // this warp's loads of the tile have landed: release the stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      mbar_wait(&rbar[k & 1], (k >> 1) & 1);
+      uint8_t* eb = wbuf + (k & 1) * 4096;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4* sp = reinterpret_cast<float4*>(eb + swz128_off(lane, j));
+        const float4 r4 = *sp;
+        *sp = make_float4(__uint_as_float(u[4 * j]) + bv[4 * j] + r4.x, __uint_as_float(u[4 * j + 1]) + bv[4 * j + 1] + r4.y,
+                          __uint_as_float(u[4 * j + 2]) + bv[4 * j + 2] + r4.z, __uint_as_float(u[4 * j + 3]) + bv[4 * j + 3] + r4.w);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmC, eb, colc, m0w, 0);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     // Two groups of four warps (4..7 and 8..11); warp w may touch TMEM lanes 32*(w%4)..+31, so each group covers
