@@ -12,6 +12,7 @@
 
 #include "../../include/af2b200.h"
 #include "attention_tc.cuh"
+#include "attention2_tc.cuh"
 #include "gemm_tc.cuh"
 #include "proj_tc.cuh"
 #include "simt_kernels.cuh"
@@ -374,12 +375,14 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
 // -------------------------------------------------------------------------------------------------
 // attention launch (one folded batch group)
 // -------------------------------------------------------------------------------------------------
+int g_attn_ver = 1;   // 1: attention_tc.cuh (default); 2: experimental split-KV / P-in-TMEM kernel attention2_tc.cuh (AF2_ATTN_VER=2)
+
 template <int DH>
-int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
-                          const CUtensorMap& tg, const AttnParams& p, cudaStream_t s) {
-  using L = AttnSmem<DH>;
+int launch_attention2_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
+                           const CUtensorMap& tg, const AttnParams& p, cudaStream_t s) {
+  using L = Attn2Smem<DH>;
   static bool configured = false;
-  auto kern = attention_tc_kernel<DH>;
+  auto kern = attention2_tc_kernel<DH>;
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
@@ -395,13 +398,35 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   return AF2_OK;
 }
 
+template <int DH>
+int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
+                          const CUtensorMap& tg, const CUtensorMap& to, const AttnParams& p, cudaStream_t s) {
+  if (g_attn_ver == 2) return launch_attention2_inst<DH>(tq, tk, tv, tbias, tg, p, s);
+  using L = AttnSmem<DH>;
+  static bool configured = false;
+  auto kern = attention_tc_kernel<DH>;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const long long items = (long long)((p.n + 127) / 128) * p.heads * p.nbatch;
+  if (items <= 0) return AF2_OK;
+  const int grid = (int)(items < sm_count() ? items : sm_count());     // persistent CTAs
+  const double tokens = (double)p.n * p.nbatch;
+  ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
+               tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
+  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, to, p);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
 // qkv: bf16 [tokens, 3I] (q | k | v), token(b', i) = b' * tok_sb + i * tok_si
 int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nbatch, long long tok_sb, long long tok_si,
                      const __nv_bfloat16* bias, int npad, const uint8_t* mask, const __nv_bfloat16* gate,
                      __nv_bfloat16* out, cudaStream_t s) {
   const long long I = (long long)heads * dh;
   const long long ld = 3 * I;
-  CUtensorMap tq, tk, tv, tb, tg;
+  CUtensorMap tq, tk, tv, tb, tg, to;
   unsigned long long dims[4] = {(unsigned long long)dh, (unsigned long long)n, (unsigned long long)heads, (unsigned long long)nbatch};
   unsigned long long str[3] = {(unsigned long long)(tok_si * ld * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * ld * 2)};
   unsigned box[4] = {(unsigned)dh, 128, 1, 1};
@@ -411,6 +436,8 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz));
   unsigned long long gstr[3] = {(unsigned long long)(tok_si * I * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * I * 2)};
   AF2_TRY(make_tmap(&tg, gate, 4, dims, gstr, box, swz));
+  unsigned obox[4] = {(unsigned)dh, 32, 1, 1};            // the output leaves per 32-row quarter of a query block
+  AF2_TRY(make_tmap(&to, out, 4, dims, gstr, obox, swz));
   if (bias) {
     unsigned long long bd[3] = {(unsigned long long)npad, (unsigned long long)n, (unsigned long long)heads};
     unsigned long long bs[2] = {(unsigned long long)npad * 2, (unsigned long long)n * npad * 2};
@@ -424,8 +451,8 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.n = n; p.heads = heads; p.nbatch = nbatch; p.has_bias = bias != nullptr;
   p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
   p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
-  if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, p, s);
-  if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, p, s);
+  if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
+  if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
 }
 
@@ -478,6 +505,7 @@ void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : 
 
 int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
+  if (const char* e = getenv("AF2_ATTN_VER")) g_attn_ver = atoi(e) == 2 ? 2 : 1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;

@@ -1,17 +1,22 @@
 // Axial self-attention with shared additive pair bias and the reference's two-sided mask, on tcgen05.
 // Replaces Attention.forward (alphafold2.py:125-190) as driven by AxialAttention (alphafold2.py:219-255).
 //
-// Persistent CTAs; a work item = one (folded batch element b', head h, block of 128 queries), ordered so that
-// concurrently running CTAs share the same (h, query block) bias tiles in L2.  Keys/values are streamed in
-// blocks of 128 through a 2-stage TMA pipeline together with the matching [128 q x 128 k] bf16 bias tile; the
-// producer runs ahead across work items (Q is double buffered), so loads of item i+1 overlap the math of item i.
+// Persistent CTAs; a work item = one (folded batch element b', head h, block of 128 queries).  Items are ordered
+// (h, query block, b') and every CTA owns a CONTIGUOUS range of them, so its items share the (h, query block) pair-bias
+// tiles: for n <= 256 those [128 q x n k] bf16 tiles stay RESIDENT in shared memory and are reloaded only when the range
+// crosses into the next (h, query block) (at most twice per CTA at C2).  That removes 64 of the 160 KB that every item
+// used to pull from L2 -- the kernel is bound by the L2 -> SM fill rate, not by the tensor pipe.  Keys/values are
+// streamed in blocks of 128 through a TMA pipeline (2 stages with a bias, 4 without; for n > 256 the bias tile of the
+// block travels with its K/V stage); the producer runs ahead across work items.
 //   S_j = Q K_j^T           tcgen05.mma  (M=128, N=128, K=DH)  -> TMEM (double buffered, 2 x 128 cols)
 //   softmax warps (8)       two threads per query row (each owns 64 of the 128 keys of the block):
 //                           TMEM -> regs, + bias + key mask, online max/sum (row max exchanged through smem),
 //                           P_j -> smem (bf16, 128B swizzle), rescale O in TMEM when the running max moves
 //   O  += P_j V_j           tcgen05.mma  (M=128, N=DH, K=128), V consumed MN-major straight from its
 //                           [key][dh] layout
-//   epilogue                O / l * sigmoid-gate -> bf16 [token, h*DH + e]
+//   epilogue                O / l * sigmoid-gate -> bf16, written IN PLACE over the gate tile in shared memory and sent
+//                           to [token, h*DH + e] by one TMA store per 32 rows (a thread-per-row STG.128 pattern
+//                           kept the LSU busy for ~1.5k cycles per item: 32 lines per instruction)
 // Logits are produced directly in the log2 domain: the host folds dim_head^-0.5 * log2(e) into to_q and
 // log2(e) into edges_to_attn_bias, so the softmax is exp2(v - max) with no per-element scaling.
 //
@@ -48,6 +53,11 @@ struct AttnSmem {
   static constexpr int P_BYTES = 128 * 128 * 2;         // two 64-key K-chunks of [128 q rows x 128 B]
   static constexpr int Q_OFF = 0;                       // Q tile of the current item
   static constexpr int G_OFF = Q_BYTES;                 // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
+  // K/V (+ bias) region of 2 * STAGE_BYTES, carved at run time:
+  //   resident bias (n <= 256): [K V] x 2 stages | bias tiles of key blocks 0, 1
+  //   streamed bias (n > 256) : [K V bias] x 2 stages
+  //   no bias                 : [K V] x 4 stages
+  static constexpr int KV_BYTES = K_BYTES + V_BYTES;
   static constexpr int STAGE_OFF = 3 * Q_BYTES;
   static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
@@ -65,7 +75,8 @@ template <int DH>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
-                    const __grid_constant__ CUtensorMap tmG, const __grid_constant__ AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmO,
+                    const __grid_constant__ AttnParams p) {
   using L = AttnSmem<DH>;
   constexpr uint32_t SWZ = (DH == 64) ? SWZ_128 : SWZ_64;
   constexpr uint32_t ROWB = DH * 2;                 // bytes per Q/K/V row
@@ -78,16 +89,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* q_full = bars + 0;     // Q tile landed
   uint64_t* g_full = bars + 1;     // [2] gate tile landed (slot it & 1)
   uint64_t* q_empty = bars + 3;    // Q tile consumed by the item's last QK^T
-  uint64_t* kv_full = bars + 4;    // [2]
-  uint64_t* kv_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;     // [2]
-  uint64_t* s_empty = bars + 10;   // [2]
-  uint64_t* p_full = bars + 12;
-  uint64_t* pv_done = bars + 13;
-  uint64_t* kb_full = bars + 14;   // [2] key-mask terms of a block staged
-  uint64_t* kb_empty = bars + 16;  // [2] ... and consumed by the 8 softmax warps
-  uint64_t* g_empty = bars + 18;   // [2] gate tile consumed by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* kv_full = bars + 4;    // [4]
+  uint64_t* kv_empty = bars + 8;   // [4]
+  uint64_t* s_full = bars + 12;    // [2]
+  uint64_t* s_empty = bars + 14;   // [2]
+  uint64_t* p_full = bars + 16;
+  uint64_t* pv_done = bars + 17;
+  uint64_t* kb_full = bars + 18;   // [2] key-mask terms of a block staged
+  uint64_t* kb_empty = bars + 20;  // [2] ... and consumed by the 8 softmax warps
+  uint64_t* g_empty = bars + 22;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
+  uint64_t* bias_full = bars + 24; // resident bias tiles of the current (h, query block) landed
+  uint64_t* bias_empty = bars + 25;// ... and no longer needed by the 8 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
   float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
@@ -99,15 +112,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nkv = (p.n + 127) / 128;
   const int nqb = nkv;
   const int total_items = nqb * p.heads * p.nbatch;
-  const int my_items = (total_items > static_cast<int>(blockIdx.x))
-                           ? (total_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-  // item id = ((h * nqb + qb) * nbatch + b'): neighbours in time differ only in b' and share the bias tile
+  // item id = ((h * nqb + qb) * nbatch + b'); this CTA owns ids [item0, item0 + my_items)
+  const int item0 = static_cast<int>(static_cast<long long>(total_items) * blockIdx.x / gridDim.x);
+  const int my_items = static_cast<int>(static_cast<long long>(total_items) * (blockIdx.x + 1) / gridDim.x) - item0;
   auto decode = [&](int it, int& qb_, int& h_, int& b_) {
-    const int id = blockIdx.x + it * gridDim.x;
+    const int id = item0 + it;
     b_ = id % p.nbatch;
     qb_ = (id / p.nbatch) % nqb;
     h_ = id / (p.nbatch * nqb);
   };
+  auto combo_of = [&](int it) { return (item0 + it) / p.nbatch; };       // (h, query block) index: selects the bias tiles
+  const bool resident = p.has_bias && nkv <= 2;
+  const int nst = p.has_bias ? 2 : 4;                                    // K/V pipeline depth
+  const int stage_stride = (p.has_bias && !resident) ? L::STAGE_BYTES : L::KV_BYTES;
+  const int bias_res_off = L::STAGE_OFF + 2 * L::KV_BYTES;               // resident tiles: + j * BIAS_BYTES
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0, O_COL = 256;
 
@@ -116,11 +134,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (p.has_bias) prefetch_tmap(&tmBias);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&g_full[s], 1);
-      mbar_init(&g_empty[s], 8);
+    prefetch_tmap(&tmO);
+    mbar_init(bias_full, 1);
+    mbar_init(bias_empty, 8);
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&g_full[s], 1);
+      mbar_init(&g_empty[s], 4);
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 8);
       mbar_init(&kb_full[s], 1);
@@ -139,29 +162,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
+      int prev_combo = -1, nc = 0;
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
         decode(it, qb, h, b);
         const int gs = it & 1;
+        if (resident && combo_of(it) != prev_combo) {
+          prev_combo = combo_of(it);
+          mbar_wait(bias_empty, (nc & 1) ^ 1);
+          mbar_arrive_expect_tx(bias_full, nkv * L::BIAS_BYTES);
+          for (int j = 0; j < nkv; ++j) {
+            uint8_t* sb = smem + bias_res_off + j * L::BIAS_BYTES;
+            tma_load_3d(sb, &tmBias, bias_full, j * 128, qb * 128, h);
+            tma_load_3d(sb + 16384, &tmBias, bias_full, j * 128 + 64, qb * 128, h);
+          }
+          ++nc;
+        }
         mbar_wait(q_empty, (it & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, L::Q_BYTES);
         tma_load_4d(smem + L::Q_OFF, &tmQ, q_full, 0, qb * 128, h, b);
         mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
         tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
+        const bool stream_bias = p.has_bias && !resident;
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
-          const int st = g & 1;
-          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
-          uint8_t* sk = smem + L::STAGE_OFF + st * L::STAGE_BYTES;
+          const int kst = g % nst;
+          mbar_wait(&kv_empty[kst], ((g / nst) & 1) ^ 1);
+          uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
           uint8_t* sv = sk + L::K_BYTES;
-          uint8_t* sbias = sv + L::V_BYTES;
-          mbar_arrive_expect_tx(&kv_full[st], L::K_BYTES + L::V_BYTES + (p.has_bias ? L::BIAS_BYTES : 0));
-          tma_load_4d(sk, &tmK, &kv_full[st], 0, j * 128, h, b);
-          tma_load_4d(sv, &tmV, &kv_full[st], 0, j * 128, h, b);
-          if (p.has_bias) {
-            tma_load_3d(sbias, &tmBias, &kv_full[st], j * 128, qb * 128, h);
-            tma_load_3d(sbias + 16384, &tmBias, &kv_full[st], j * 128 + 64, qb * 128, h);
+          mbar_arrive_expect_tx(&kv_full[kst], L::KV_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
+          tma_load_4d(sk, &tmK, &kv_full[kst], 0, j * 128, h, b);
+          tma_load_4d(sv, &tmV, &kv_full[kst], 0, j * 128, h, b);
+          if (stream_bias) {
+            uint8_t* sbias = sv + L::V_BYTES;
+            tma_load_3d(sbias, &tmBias, &kv_full[kst], j * 128, qb * 128, h);
+            tma_load_3d(sbias + 16384, &tmBias, &kv_full[kst], j * 128 + 64, qb * 128, h);
           }
         }
       }
@@ -174,14 +210,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int total_blocks = my_items * nkv;
     auto issue_s = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
-      const int st = g & 1;
+      const int st = g & 1, kst = g % nst;
       if (j == 0) mbar_wait(q_full, it & 1);
-      mbar_wait(&kv_full[st], (g >> 1) & 1);
+      mbar_wait(&kv_full[kst], (g / nst) & 1);
       mbar_wait(&s_empty[st], ((g >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF);
-        const uint32_t sk = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES);
+        const uint32_t sk = smem_u32(smem + L::STAGE_OFF + kst * stage_stride);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
           const uint64_t ad = umma_smem_desc(sq + k * 32, 16, SBO, SWZ);
@@ -193,14 +229,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     };
+    // can S(g) be issued without blocking?  (Q of a new item, the K/V stage and the S buffer are all ready)
+    auto s_ready = [&](int g) {
+      const int it = g / nkv, j = g - it * nkv;
+      if (j == 0 && !mbar_test(q_full, it & 1)) return false;
+      if (!mbar_test(&kv_full[g % nst], (g / nst) & 1)) return false;
+      return mbar_test(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
+    };
     if (total_blocks > 0) issue_s(0);
     for (int g = 0; g < total_blocks; ++g) {
-      const int st = g & 1;
-      if (g + 1 < total_blocks) issue_s(g + 1);
-      mbar_wait(p_full, g & 1);
+      // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
+      bool s_issued = g + 1 >= total_blocks;
+      while (!mbar_test(p_full, g & 1)) {
+        if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
+      }
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES);
+        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
         const bool first = (g % nkv) == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -210,10 +255,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
           umma_bf16(tmem_base + O_COL, ad, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&kv_empty[g % nst]);
         umma_commit(pv_done);
       }
       __syncwarp();
+      if (!s_issued) issue_s(g + 1);
     }
   } else if (warp == 10) {
     // ================================ key-mask warp ================================
@@ -261,12 +307,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool o_owner = O_OWNER_ALL || hk == 0;
     const uint32_t o_col = O_COL + (O_OWNER_ALL ? hk * 32 : 0);
 
+    int prev_combo = -1, nc = 0;
     for (int it = 0; it < my_items; ++it) {
     int qb, h, b;
     decode(it, qb, h, b);
-    const int qi = qb * 128 + r;
-    const bool q_in = qi < p.n;
     bool q_valid = true;
+    if (resident && combo_of(it) != prev_combo) {       // this CTA's range entered the next (h, query block): new bias tiles
+      prev_combo = combo_of(it);
+      mbar_wait(bias_full, nc & 1);
+      ++nc;
+    }
 
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
@@ -294,7 +344,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(&s_empty[st]);
 
       // logits (log2 domain) = s + bias + keyterm
-      const uint8_t* sbias = smem + L::STAGE_OFF + st * L::STAGE_BYTES + L::K_BYTES + L::V_BYTES + hk * 16384;
+      const uint8_t* sbias = smem + (resident ? bias_res_off + j * L::BIAS_BYTES
+                                              : L::STAGE_OFF + (g % nst) * L::STAGE_BYTES + L::KV_BYTES) + hk * 16384;
       const float* kbs = keyb + st * 128 + hk * 64;
       const bool keys_masked = kflag[st] != 0u;      // block-uniform: most blocks have every key usable
       float mx0 = NEG_INF, mx1 = NEG_INF;
@@ -378,6 +429,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      // the previous item's output tile has had a whole key block of time to drain: hand its gate slot back to the producer
+      if (j == 0 && it > 0 && hk == 0 && lane == 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&g_empty[(it - 1) & 1]);
+      }
+    }
+    if (resident && (it + 1 == my_items || combo_of(it + 1) != prev_combo)) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bias_empty);           // last item of this (h, query block): the bias tiles may be replaced
     }
 
     // ---- epilogue: O / l * gate -> out ----
@@ -387,17 +447,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(pv_done, (it * nkv + nkv - 1) & 1);
     tc_fence_after();
     mbar_wait(&g_full[it & 1], (it >> 1) & 1);
+    uint8_t* gt = smem + L::G_OFF + (it & 1) * L::Q_BYTES;
     if (o_owner) {
-      const long long tok = b * p.tok_sb + static_cast<long long>(qi) * p.tok_si;
-      const int cbase = h * DH + (O_OWNER_ALL ? hk * 32 : 0);
-      __nv_bfloat16* op = p.out + tok * p.ld_out + cbase;
-      const uint8_t* gt = smem + L::G_OFF + (it & 1) * L::Q_BYTES;
       uint32_t o[32];
       tmem_ld32(tmem_base + o_col + lane_sel, o);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32)
+        // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32); the gated output
+        // replaces the gate values it was computed from, in the same (swizzled) place
         const uint32_t goff = (DH == 64) ? swz128_off(r, hk * 4 + i) : (r * 64u + ((static_cast<uint32_t>(i) ^ ((r >> 1) & 3u)) << 4));
         const uint4 gq = *reinterpret_cast<const uint4*>(gt + goff);
         const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
@@ -408,13 +466,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float bb = __uint_as_float(o[8 * i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
           ow[t] = pack_bf16x2(a, bb);
         }
-        if (q_in) *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(gt + goff) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&g_empty[it & 1]);
     tc_fence_before();            // O has been read: order it before the next item's first P V
+    fence_proxy_async_smem();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both column halves of these 32 rows are in the tile
+    if (hk == 0 && lane == 0) {
+      // rows beyond n are clipped by the tensor map
+      tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
+      tma_store_commit();
+    }
     }  // work items
+    if (hk == 0 && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last output store
   }
 
   tc_fence_before();

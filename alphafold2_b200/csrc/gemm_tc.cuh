@@ -67,17 +67,6 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;       // barriers + 1 KB alignment slack
 };
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_SIGMOID) return sigmoidf_fast(x);
   if (act == ACT_GELU) return gelu_erf(x);
