@@ -8,12 +8,16 @@
 // used to pull from L2 -- the kernel is bound by the L2 -> SM fill rate, not by the tensor pipe.  Keys/values are
 // streamed in blocks of 128 through a TMA pipeline (2 stages with a bias, 4 without; for n > 256 the bias tile of the
 // block travels with its K/V stage); the producer runs ahead across work items.
-//   S_j = Q K_j^T           tcgen05.mma  (M=128, N=128, K=DH)  -> TMEM (double buffered, 2 x 128 cols)
+//   S_j = Q K_j^T + I B_j   tcgen05.mma  (M=128, N=128, K=DH, then K=128 against a constant identity tile): the pair bias
+//                           tile B_j [query][key] is the MN-major B operand, so the TENSOR CORE adds the bias and the
+//                           softmax threads never load / unpack / add it  -> TMEM (double buffered, 2 x 128 cols)
 //   softmax warps (8)       two threads per query row (each owns 64 of the 128 keys of the block):
-//                           TMEM -> regs, + bias + key mask, online max/sum (row max exchanged through smem),
-//                           P_j -> smem (bf16, 128B swizzle), rescale O in TMEM when the running max moves
-//   O  += P_j V_j           tcgen05.mma  (M=128, N=DH, K=128), V consumed MN-major straight from its
-//                           [key][dh] layout
+//                           TMEM -> regs, (+ key mask), online max/sum (row max exchanged through smem),
+//                           P_j -> packed bf16 written back over the S columns it came from (tcgen05.st); O is
+//                           rescaled in TMEM only when the running max moves by more than 2^8
+//   O  += P_j V_j           tcgen05.mma with A = P_j read FROM TENSOR MEMORY (M=128, N=DH, K=128), V consumed MN-major
+//                           straight from its [key][dh] layout.  No P tile in shared memory, no proxy fence per block,
+//                           and P is double buffered with S, so the softmax never waits for the previous P V.
 //   epilogue                O / l * sigmoid-gate -> bf16, written IN PLACE over the gate tile in shared memory and sent
 //                           to [token, h*DH + e] by one TMA store per 32 rows (a thread-per-row STG.128 pattern
 //                           kept the LSU busy for ~1.5k cycles per item: 32 lines per instruction)
@@ -50,7 +54,7 @@ struct AttnSmem {
   static constexpr int V_BYTES = 128 * DH * 2;
   static constexpr int BIAS_BYTES = 128 * 128 * 2;      // two 64-key boxes of [128 q rows x 128 B]
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BIAS_BYTES;
-  static constexpr int P_BYTES = 128 * 128 * 2;         // two 64-key K-chunks of [128 q rows x 128 B]
+  static constexpr int IDENT_BYTES = 128 * 128 * 2;     // identity [128 x 128] bf16, K-major SW128 (two 64-column halves)
   static constexpr int Q_OFF = 0;                       // Q tile of the current item
   static constexpr int G_OFF = Q_BYTES;                 // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
   // K/V (+ bias) region of 2 * STAGE_BYTES, carved at run time:
@@ -59,8 +63,8 @@ struct AttnSmem {
   //   no bias                 : [K V] x 4 stages
   static constexpr int KV_BYTES = K_BYTES + V_BYTES;
   static constexpr int STAGE_OFF = 3 * Q_BYTES;
-  static constexpr int P_OFF = STAGE_OFF + 2 * STAGE_BYTES;
-  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr int IDENT_OFF = STAGE_OFF + 2 * STAGE_BYTES;
+  static constexpr int BAR_OFF = IDENT_OFF + IDENT_BYTES;
   static constexpr int KB_OFF = BAR_OFF + 256;          // float key term (0 / -inf) [2][128]
   static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
   static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
@@ -92,14 +96,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* kv_full = bars + 4;    // [4]
   uint64_t* kv_empty = bars + 8;   // [4]
   uint64_t* s_full = bars + 12;    // [2]
-  uint64_t* s_empty = bars + 14;   // [2]
-  uint64_t* p_full = bars + 16;
+  uint64_t* p_full = bars + 14;    // [2] P of the block is in its S buffer
   uint64_t* pv_done = bars + 17;
   uint64_t* kb_full = bars + 18;   // [2] key-mask terms of a block staged
   uint64_t* kb_empty = bars + 20;  // [2] ... and consumed by the 8 softmax warps
   uint64_t* g_empty = bars + 22;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
   uint64_t* bias_full = bars + 24; // resident bias tiles of the current (h, query block) landed
-  uint64_t* bias_empty = bars + 25;// ... and no longer needed by the 8 softmax warps
+  uint64_t* bias_empty = bars + 25;// ... and consumed by the last S MMA of that (h, query block)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
@@ -136,7 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_empty, 1);
     prefetch_tmap(&tmO);
     mbar_init(bias_full, 1);
-    mbar_init(bias_empty, 8);
+    mbar_init(bias_empty, 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -145,15 +148,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&g_full[s], 1);
       mbar_init(&g_empty[s], 4);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 8);
       mbar_init(&kb_full[s], 1);
       mbar_init(&kb_empty[s], 8);
     }
-    mbar_init(p_full, 8);
+    mbar_init(&p_full[0], 8);
+    mbar_init(&p_full[1], 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (p.has_bias) {
+    // identity tile: element (r, c) lives in half c / 64 at r * 128 + (((c % 64) / 8) ^ (r & 7)) * 16 + (c % 8) * 2
+    uint4* id4 = reinterpret_cast<uint4*>(smem + L::IDENT_OFF);
+    for (int i = threadIdx.x; i < L::IDENT_BYTES / 16; i += ATTN_THREADS) id4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const uint32_t rc = threadIdx.x;
+      *reinterpret_cast<__nv_bfloat16*>(smem + L::IDENT_OFF + (rc >> 6) * 16384 + rc * 128 + ((((rc & 63) >> 3) ^ (rc & 7)) << 4) + (rc & 7) * 2) =
+          __float2bfloat16(1.0f);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -205,15 +220,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, V is MN-major
-    const uint32_t sp = smem_u32(smem + L::P_OFF);
+    constexpr uint32_t idesc_b = umma_idesc_bf16(128, 128, 0, 1);   // S += I B: identity K-major, bias tile MN-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, P from tensor memory, V MN-major
     const int total_blocks = my_items * nkv;
+    int prev_combo = -1, nc = 0;
     auto issue_s = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
       const int st = g & 1, kst = g % nst;
-      if (j == 0) mbar_wait(q_full, it & 1);
+      if (j == 0) {
+        mbar_wait(q_full, it & 1);
+        if (resident && combo_of(it) != prev_combo) {     // this CTA's range entered the next (h, query block): new bias tiles
+          prev_combo = combo_of(it);
+          mbar_wait(bias_full, nc & 1);
+          ++nc;
+        }
+      }
       mbar_wait(&kv_full[kst], (g / nst) & 1);
-      mbar_wait(&s_empty[st], ((g >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF);
@@ -224,23 +246,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t bd = umma_smem_desc(sk + k * 32, 16, SBO, SWZ);
           umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_s, k != 0 ? 1u : 0u);
         }
+        if (p.has_bias) {
+          const uint32_t si = smem_u32(smem + L::IDENT_OFF);
+          // bias tile of key block j: [128 query rows x 128 B] x two 64-key boxes
+          const uint32_t sbz = resident ? smem_u32(smem + bias_res_off + j * L::BIAS_BYTES) : sk + L::KV_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // A: identity columns 16k .. 16k+15 (K-major, 64-column halves 16 KB apart)
+            const uint64_t ad = umma_smem_desc(si + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128);
+            // B: bias rows (the K index) 16k .. 16k+15 with the keys contiguous (MN-major): 8-row atoms 1024 B apart,
+            // the two 64-key boxes 16 KB apart
+            const uint64_t bd = umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
+            umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_b, 1u);
+          }
+        }
         umma_commit(&s_full[st]);
-        if (j == nkv - 1) umma_commit(q_empty);          // Q buffer reusable once the item's last QK^T retires
+        if (j == nkv - 1) {
+          umma_commit(q_empty);                            // Q buffer reusable once the item's last QK^T retires
+          if (resident && (it + 1 == my_items || combo_of(it + 1) != prev_combo)) umma_commit(bias_empty);
+        }
       }
       __syncwarp();
     };
-    // can S(g) be issued without blocking?  (Q of a new item, the K/V stage and the S buffer are all ready)
+    // can S(g) be issued without blocking?  (Q / bias of a new item and the K/V stage have landed; the S buffer itself is
+    // free by construction: S(g) is issued after P V(g-2), and the tensor core executes in issue order)
     auto s_ready = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
-      if (j == 0 && !mbar_test(q_full, it & 1)) return false;
-      if (!mbar_test(&kv_full[g % nst], (g / nst) & 1)) return false;
-      return mbar_test(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
+      if (j == 0) {
+        if (!mbar_test(q_full, it & 1)) return false;
+        if (resident && combo_of(it) != prev_combo && !mbar_test(bias_full, nc & 1)) return false;
+      }
+      return mbar_test(&kv_full[g % nst], (g / nst) & 1);
     };
     if (total_blocks > 0) issue_s(0);
     for (int g = 0; g < total_blocks; ++g) {
+      const int st = g & 1;
       // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
       bool s_issued = g + 1 >= total_blocks;
-      while (!mbar_test(p_full, g & 1)) {
+      while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
       tc_fence_after();
@@ -249,11 +292,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool first = (g % nkv) == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          // A = P: two 64-key chunks of 16 KB, K step 32 B inside a chunk
-          const uint64_t ad = umma_smem_desc(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128);
-          // B = V [key][dh], MN-major: 16 keys = 2 swizzle atoms of 8 key-rows
+          // A = P [128 rows x 16 keys] = 8 packed columns of the S / P buffer; B = V [key][dh], MN-major: 16 keys = 2 atoms
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
-          umma_bf16(tmem_base + O_COL, ad, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + O_COL, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
         }
         umma_commit(&kv_empty[g % nst]);
         umma_commit(pv_done);
@@ -307,16 +348,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool o_owner = O_OWNER_ALL || hk == 0;
     const uint32_t o_col = O_COL + (O_OWNER_ALL ? hk * 32 : 0);
 
-    int prev_combo = -1, nc = 0;
     for (int it = 0; it < my_items; ++it) {
     int qb, h, b;
     decode(it, qb, h, b);
     bool q_valid = true;
-    if (resident && combo_of(it) != prev_combo) {       // this CTA's range entered the next (h, query block): new bias tiles
-      prev_combo = combo_of(it);
-      mbar_wait(bias_full, nc & 1);
-      ++nc;
-    }
 
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
@@ -339,26 +374,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           s[32 + i] = __uint_as_float(u1[i]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
 
-      // logits (log2 domain) = s + bias + keyterm
-      const uint8_t* sbias = smem + (resident ? bias_res_off + j * L::BIAS_BYTES
-                                              : L::STAGE_OFF + (g % nst) * L::STAGE_BYTES + L::KV_BYTES) + hk * 16384;
+      // logits (log2 domain) = s (pair bias included by the tensor core) + keyterm
       const float* kbs = keyb + st * 128 + hk * 64;
       const bool keys_masked = kflag[st] != 0u;      // block-uniform: most blocks have every key usable
       float mx0 = NEG_INF, mx1 = NEG_INF;
-      if (p.has_bias) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {       // 8 chunks of 8 keys
-          const uint4 raw = *reinterpret_cast<const uint4*>(sbias + swz128_off(r, c));
-          s[c * 8 + 0] += bf16lo_to_f32(raw.x); s[c * 8 + 1] += bf16hi_to_f32(raw.x);
-          s[c * 8 + 2] += bf16lo_to_f32(raw.y); s[c * 8 + 3] += bf16hi_to_f32(raw.y);
-          s[c * 8 + 4] += bf16lo_to_f32(raw.z); s[c * 8 + 5] += bf16hi_to_f32(raw.z);
-          s[c * 8 + 6] += bf16lo_to_f32(raw.w); s[c * 8 + 7] += bf16hi_to_f32(raw.w);
-        }
-      }
       if (keys_masked) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -403,41 +423,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l_run = l_run * corr + (ls0 + ls1);
       m_run = m_new;
 
-      // previous P V must be complete before O is rescaled and before P smem is overwritten
-      if (j > 0) {
+      // the previous P V must have retired before O is rescaled (rare: the running maximum moved by more than 2^8)
+      if (j > 0 && rescale) {
         mbar_wait(pv_done, (g - 1) & 1);
         tc_fence_after();
-        if (o_owner && rescale) {
+        if (o_owner) {
           uint32_t o[32];
           tmem_ld32(tmem_base + o_col + lane_sel, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
           tmem_st32(tmem_base + o_col + lane_sel, o);
-          tmem_st_wait();
         }
       }
-      // P_j -> smem, bf16, K-major 128B swizzle (this thread's 64-key chunk)
-      uint8_t* spb = smem + L::P_OFF + hk * 16384;
+      // P_j -> tensor memory: this thread's 64 keys become 32 packed columns [hk*32, hk*32+32) of the S buffer.  Those
+      // columns held logits of the hk = 0 half, which its owner loaded before the row-max barrier above.
+      {
+        uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 pk = make_uint4(pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]), pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]),
-                              pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]), pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
-        *reinterpret_cast<uint4*>(spb + swz128_off(r, c)) = pk;
+        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16x2(s[2 * c], s[2 * c + 1]);
+        tmem_st32(tmem_base + S_COL + st * 128 + hk * 32 + lane_sel, pk);
       }
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[st]);
       // the previous item's output tile has had a whole key block of time to drain: hand its gate slot back to the producer
       if (j == 0 && it > 0 && hk == 0 && lane == 0) {
         tma_store_wait_read<0>();
         mbar_arrive(&g_empty[(it - 1) & 1]);
       }
-    }
-    if (resident && (it + 1 == my_items || combo_of(it + 1) != prev_combo)) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bias_empty);           // last item of this (h, query block): the bias tiles may be replaced
     }
 
     // ---- epilogue: O / l * gate -> out ----
