@@ -393,7 +393,7 @@ int launch_attention2_inst(const CUtensorMap& tq, const CUtensorMap& tk, const C
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
-  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, p);
+  kern<<<grid, ATTN2_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, p);
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }

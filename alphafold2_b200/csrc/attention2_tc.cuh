@@ -24,6 +24,8 @@
 
 namespace af2 {
 
+constexpr int ATTN2_THREADS = 352;   // TMA warp, MMA warp, 2 x 4 softmax warps, key-mask warp
+
 template <int DH>
 struct Attn2Smem {
   static constexpr int Q_BYTES = 128 * DH * 2;
@@ -44,7 +46,7 @@ struct Attn2Smem {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+__global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
                      const __grid_constant__ CUtensorMap tmG, const __grid_constant__ AttnParams p) {
@@ -111,7 +113,7 @@ attention2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (p.has_bias) {
     // identity tile: element (r, c) of half c/64 at r*128 + (((c%64)/8) ^ (r&7))*16 + (c%8)*2
     uint4* id4 = reinterpret_cast<uint4*>(smem + L::IDENT_OFF);
-    for (int i = threadIdx.x; i < 2048; i += ATTN_THREADS) id4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 2048; i += ATTN2_THREADS) id4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (threadIdx.x < 128) {
       const uint32_t r = threadIdx.x, c = threadIdx.x;

@@ -45,7 +45,7 @@ struct AttnParams {
   long long ld_gate, ld_out;
 };
 
-constexpr int ATTN_THREADS = 352;   // TMA warp, MMA warp, 8 softmax warps, key-mask warp
+constexpr int ATTN_THREADS = 384;   // Q/G/K/bias TMA warp, MMA warp, 8 softmax warps, key-mask warp, V TMA warp
 
 template <int DH>
 struct AttnSmem {
@@ -54,18 +54,22 @@ struct AttnSmem {
   static constexpr int V_BYTES = 128 * DH * 2;
   static constexpr int BIAS_BYTES = 128 * 128 * 2;      // two 64-key boxes of [128 q rows x 128 B]
   static constexpr int STAGE_BYTES = K_BYTES + V_BYTES + BIAS_BYTES;
-  static constexpr int IDENT_BYTES = 128 * 128 * 2;     // identity [128 x 128] bf16, K-major SW128 (two 64-column halves)
-  static constexpr int Q_OFF = 0;                       // Q tile of the current item
-  static constexpr int G_OFF = Q_BYTES;                 // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
+  // Identity operand of the bias MMA.  K step k needs A_k[r][e] = (r == 16k + e): only the two 8-row groups 2k, 2k+1 are
+  // non-zero and they look the same for every k, so ONE strip of 30 row groups (32-byte swizzle atoms of 8 rows x 16
+  // columns, 256 B each) -- 14 zero groups, the two diagonal groups, 14 zero groups -- serves all eight steps: step k
+  // starts its descriptor (14 - 2k) groups into the strip.
+  static constexpr int IDENT_BYTES = 32 * 256;
+  static constexpr int Q_OFF = 0;                       // [2] Q tiles (slot it & 1)
+  static constexpr int G_OFF = 2 * Q_BYTES;             // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
   // K/V (+ bias) region of 2 * STAGE_BYTES, carved at run time:
   //   resident bias (n <= 256): [K V] x 2 stages | bias tiles of key blocks 0, 1
   //   streamed bias (n > 256) : [K V bias] x 2 stages
   //   no bias                 : [K V] x 4 stages
   static constexpr int KV_BYTES = K_BYTES + V_BYTES;
-  static constexpr int STAGE_OFF = 3 * Q_BYTES;
+  static constexpr int STAGE_OFF = 4 * Q_BYTES;
   static constexpr int IDENT_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = IDENT_OFF + IDENT_BYTES;
-  static constexpr int KB_OFF = BAR_OFF + 256;          // float key term (0 / -inf) [2][128]
+  static constexpr int KB_OFF = BAR_OFF + 320;          // float key term (0 / -inf) [2][128]
   static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
   static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
   static constexpr int QV_OFF = L_OFF + 2 * 128 * 4;    // query-mask bytes [2][128]
@@ -90,20 +94,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* q_full = bars + 0;     // Q tile landed
-  uint64_t* g_full = bars + 1;     // [2] gate tile landed (slot it & 1)
-  uint64_t* q_empty = bars + 3;    // Q tile consumed by the item's last QK^T
-  uint64_t* kv_full = bars + 4;    // [4]
-  uint64_t* kv_empty = bars + 8;   // [4]
-  uint64_t* s_full = bars + 12;    // [2]
-  uint64_t* p_full = bars + 14;    // [2] P of the block is in its S buffer
-  uint64_t* pv_done = bars + 17;
-  uint64_t* kb_full = bars + 18;   // [2] key-mask terms of a block staged
-  uint64_t* kb_empty = bars + 20;  // [2] ... and consumed by the 8 softmax warps
-  uint64_t* g_empty = bars + 22;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
-  uint64_t* bias_full = bars + 24; // resident bias tiles of the current (h, query block) landed
-  uint64_t* bias_empty = bars + 25;// ... and consumed by the last S MMA of that (h, query block)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* q_full = bars + 0;     // [2] Q tile landed (slot it & 1)
+  uint64_t* g_full = bars + 2;     // [2] gate tile landed (slot it & 1)
+  uint64_t* q_empty = bars + 4;    // [2] Q tile consumed by the item's last QK^T
+  uint64_t* k_full = bars + 6;     // [4] K (+ streamed bias) of a block landed
+  uint64_t* k_empty = bars + 10;   // [4] ... and consumed by the block's S MMAs
+  uint64_t* v_full = bars + 14;    // [4] V of a block landed
+  uint64_t* v_empty = bars + 18;   // [4] ... and consumed by the block's P V
+  uint64_t* s_full = bars + 22;    // [2]
+  uint64_t* p_full = bars + 24;    // [2] P of the block is in its S buffer
+  uint64_t* pv_done = bars + 26;
+  uint64_t* kb_full = bars + 27;   // [2] key-mask terms of a block staged
+  uint64_t* kb_empty = bars + 29;  // [2] ... and consumed by the 8 softmax warps
+  uint64_t* g_empty = bars + 31;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
+  uint64_t* bias_full = bars + 33; // resident bias tiles of the current (h, query block) landed
+  uint64_t* bias_empty = bars + 34;// ... and consumed by the last S MMA of that (h, query block)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
   float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
@@ -135,16 +141,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmG);
     if (p.has_bias) prefetch_tmap(&tmBias);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
     prefetch_tmap(&tmO);
     mbar_init(bias_full, 1);
     mbar_init(bias_empty, 1);
     for (int s = 0; s < 4; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&g_full[s], 1);
       mbar_init(&g_empty[s], 4);
       mbar_init(&s_full[s], 1);
@@ -158,13 +166,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   if (p.has_bias) {
-    // identity tile: element (r, c) lives in half c / 64 at r * 128 + (((c % 64) / 8) ^ (r & 7)) * 16 + (c % 8) * 2
     uint4* id4 = reinterpret_cast<uint4*>(smem + L::IDENT_OFF);
     for (int i = threadIdx.x; i < L::IDENT_BYTES / 16; i += ATTN_THREADS) id4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    if (threadIdx.x < 128) {
-      const uint32_t rc = threadIdx.x;
-      *reinterpret_cast<__nv_bfloat16*>(smem + L::IDENT_OFF + (rc >> 6) * 16384 + rc * 128 + ((((rc & 63) >> 3) ^ (rc & 7)) << 4) + (rc & 7) * 2) =
+    if (threadIdx.x < 16) {
+      // diagonal element i of the 16 x 16 block: row group 14 + i / 8, row r = i % 8, column i (16-byte chunk i / 8,
+      // XOR-ed with bit 7 of the byte address = r >> 2 by the 32-byte swizzle)
+      const uint32_t i = threadIdx.x, r = i & 7, c = i >> 3;
+      *reinterpret_cast<__nv_bfloat16*>(smem + L::IDENT_OFF + (14 + c) * 256 + r * 32 + ((c ^ (r >> 2)) << 4) + (i & 7) * 2) =
           __float2bfloat16(1.0f);
     }
     fence_proxy_async_smem();
@@ -193,9 +202,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           ++nc;
         }
-        mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-        tma_load_4d(smem + L::Q_OFF, &tmQ, q_full, 0, qb * 128, h, b);
+        mbar_wait(&q_empty[gs], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[gs], L::Q_BYTES);
+        tma_load_4d(smem + L::Q_OFF + gs * L::Q_BYTES, &tmQ, &q_full[gs], 0, qb * 128, h, b);
         mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
         tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
@@ -203,17 +212,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
           const int kst = g % nst;
-          mbar_wait(&kv_empty[kst], ((g / nst) & 1) ^ 1);
+          // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
+          mbar_wait(&k_empty[kst], ((g / nst) & 1) ^ 1);
           uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
-          uint8_t* sv = sk + L::K_BYTES;
-          mbar_arrive_expect_tx(&kv_full[kst], L::KV_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
-          tma_load_4d(sk, &tmK, &kv_full[kst], 0, j * 128, h, b);
-          tma_load_4d(sv, &tmV, &kv_full[kst], 0, j * 128, h, b);
+          mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
+          tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
           if (stream_bias) {
-            uint8_t* sbias = sv + L::V_BYTES;
-            tma_load_3d(sbias, &tmBias, &kv_full[kst], j * 128, qb * 128, h);
-            tma_load_3d(sbias + 16384, &tmBias, &kv_full[kst], j * 128 + 64, qb * 128, h);
+            uint8_t* sbias = sk + L::KV_BYTES;
+            tma_load_3d(sbias, &tmBias, &k_full[kst], j * 128, qb * 128, h);
+            tma_load_3d(sbias + 16384, &tmBias, &k_full[kst], j * 128 + 64, qb * 128, h);
           }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // ================================ V producer ==================================
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        int qb, h, b;
+        decode(it, qb, h, b);
+        for (int j = 0; j < nkv; ++j) {
+          const int g = it * nkv + j;
+          const int kst = g % nst;
+          mbar_wait(&v_empty[kst], ((g / nst) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
+          tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
         }
       }
     }
@@ -228,17 +251,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int it = g / nkv, j = g - it * nkv;
       const int st = g & 1, kst = g % nst;
       if (j == 0) {
-        mbar_wait(q_full, it & 1);
+        mbar_wait(&q_full[it & 1], (it >> 1) & 1);
         if (resident && combo_of(it) != prev_combo) {     // this CTA's range entered the next (h, query block): new bias tiles
           prev_combo = combo_of(it);
           mbar_wait(bias_full, nc & 1);
           ++nc;
         }
       }
-      mbar_wait(&kv_full[kst], (g / nst) & 1);
+      mbar_wait(&k_full[kst], (g / nst) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sq = smem_u32(smem + L::Q_OFF);
+        const uint32_t sq = smem_u32(smem + L::Q_OFF + (it & 1) * L::Q_BYTES);
         const uint32_t sk = smem_u32(smem + L::STAGE_OFF + kst * stage_stride);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -252,8 +275,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t sbz = resident ? smem_u32(smem + bias_res_off + j * L::BIAS_BYTES) : sk + L::KV_BYTES;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // A: identity columns 16k .. 16k+15 (K-major, 64-column halves 16 KB apart)
-            const uint64_t ad = umma_smem_desc(si + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128);
+            // A: identity columns 16k .. 16k+15 = the diagonal strip entered (14 - 2k) row groups in (see AttnSmem)
+            const uint64_t ad = umma_smem_desc(si + (14 - 2 * k) * 256, 16, 256, SWZ_32);
             // B: bias rows (the K index) 16k .. 16k+15 with the keys contiguous (MN-major): 8-row atoms 1024 B apart,
             // the two 64-key boxes 16 KB apart
             const uint64_t bd = umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
@@ -261,8 +284,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         umma_commit(&s_full[st]);
+        umma_commit(&k_empty[kst]);
         if (j == nkv - 1) {
-          umma_commit(q_empty);                            // Q buffer reusable once the item's last QK^T retires
+          umma_commit(&q_empty[it & 1]);                   // Q slot reusable once the item's last QK^T retires
           if (resident && (it + 1 == my_items || combo_of(it + 1) != prev_combo)) umma_commit(bias_empty);
         }
       }
@@ -273,10 +297,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto s_ready = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
       if (j == 0) {
-        if (!mbar_test(q_full, it & 1)) return false;
+        if (!mbar_test(&q_full[it & 1], (it >> 1) & 1)) return false;
         if (resident && combo_of(it) != prev_combo && !mbar_test(bias_full, nc & 1)) return false;
       }
-      return mbar_test(&kv_full[g % nst], (g / nst) & 1);
+      return mbar_test(&k_full[g % nst], (g / nst) & 1);
     };
     if (total_blocks > 0) issue_s(0);
     for (int g = 0; g < total_blocks; ++g) {
@@ -286,6 +310,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
+      mbar_wait(&v_full[g % nst], (g / nst) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
@@ -296,7 +321,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
           umma_bf16_ts(tmem_base + O_COL, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[g % nst]);
+        umma_commit(&v_empty[g % nst]);
         umma_commit(pv_done);
       }
       __syncwarp();
