@@ -11,16 +11,20 @@
 //   S_j = Q K_j^T + I B_j   tcgen05.mma  (M=128, N=128, K=DH, then K=128 against a constant identity tile): the pair bias
 //                           tile B_j [query][key] is the MN-major B operand, so the TENSOR CORE adds the bias and the
 //                           softmax threads never load / unpack / add it  -> TMEM (double buffered, 2 x 128 cols)
-//   softmax warps (8)       two threads per query row (each owns 64 of the 128 keys of the block):
+//   softmax warps (16)      four threads per query row (each owns 32 of the 128 keys of the block; the phases of a block
+//                           -- TMEM load, max, exchange, 2^x on the MUFU, pack, TMEM store -- are latency chains, and
+//                           four warps per scheduler overlap them where two could not):
 //                           TMEM -> regs, (+ key mask), online max/sum (row max exchanged through smem),
 //                           P_j -> packed bf16 written back over the S columns it came from (tcgen05.st); O is
 //                           rescaled in TMEM only when the running max moves by more than 2^8
 //   O  += P_j V_j           tcgen05.mma with A = P_j read FROM TENSOR MEMORY (M=128, N=DH, K=128), V consumed MN-major
 //                           straight from its [key][dh] layout.  No P tile in shared memory, no proxy fence per block,
 //                           and P is double buffered with S, so the softmax never waits for the previous P V.
-//   epilogue                O / l * sigmoid-gate -> bf16, written IN PLACE over the gate tile in shared memory and sent
-//                           to [token, h*DH + e] by one TMA store per 32 rows (a thread-per-row STG.128 pattern
-//                           kept the LSU busy for ~1.5k cycles per item: 32 lines per instruction)
+//   epilogue warps (4)      O is double buffered in TMEM, so the softmax warps hand a finished item over (row sums through
+//                           smem, O through the o_full barrier committed behind the item's last P V) and start the next
+//                           item at once; the epilogue warps compute O / l * sigmoid-gate -> bf16 IN PLACE over the gate
+//                           tile in shared memory and send it to [token, h*DH + e] with one TMA store per 32 rows (a
+//                           thread-per-row STG.128 pattern kept the LSU busy for ~1.5k cycles per item)
 // Logits are produced directly in the log2 domain: the host folds dim_head^-0.5 * log2(e) into to_q and
 // log2(e) into edges_to_attn_bias, so the softmax is exp2(v - max) with no per-element scaling.
 //
@@ -45,7 +49,13 @@ struct AttnParams {
   long long ld_gate, ld_out;
 };
 
-constexpr int ATTN_THREADS = 384;   // Q/G/K/bias TMA warp, MMA warp, 8 softmax warps, key-mask warp, V TMA warp
+constexpr int ATTN_NSPLIT = 4;                      // softmax threads per query row (each owns 128 / NSPLIT keys of a block)
+constexpr int ATTN_SM_WARPS = 4 * ATTN_NSPLIT;      // softmax warps 2 .. 2 + ATTN_SM_WARPS - 1
+constexpr int ATTN_W_KEYMASK = 2 + ATTN_SM_WARPS;   // then: key-mask warp, V TMA warp, 4 epilogue warps
+constexpr int ATTN_W_VPROD = ATTN_W_KEYMASK + 1;
+constexpr int ATTN_W_EPI = ATTN_W_VPROD + 1;        // a multiple of 4, so warp & 3 is the TMEM lane quarter of an epilogue warp
+constexpr int ATTN_THREADS = (ATTN_W_EPI + 4) * 32;
+static_assert(ATTN_W_EPI % 4 == 0, "epilogue warps must start at a multiple of 4");
 
 template <int DH>
 struct AttnSmem {
@@ -69,10 +79,10 @@ struct AttnSmem {
   static constexpr int STAGE_OFF = 4 * Q_BYTES;
   static constexpr int IDENT_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = IDENT_OFF + IDENT_BYTES;
-  static constexpr int KB_OFF = BAR_OFF + 320;          // float key term (0 / -inf) [2][128]
-  static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max / row-sum exchange [2][128]
-  static constexpr int L_OFF = MX_OFF + 2 * 128 * 4;    // float row-sum exchange [2][128]
-  static constexpr int QV_OFF = L_OFF + 2 * 128 * 4;    // query-mask bytes [2][128]
+  static constexpr int KB_OFF = BAR_OFF + 384;          // float key term (0 / -inf) [2][128]
+  static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max exchange [2 block parities][NSPLIT][128]
+  static constexpr int L_OFF = MX_OFF + 2 * ATTN_NSPLIT * 128 * 4;   // float row sums handed to the epilogue warps [2 slots][NSPLIT][128]
+  static constexpr int QV_OFF = L_OFF + 2 * ATTN_NSPLIT * 128 * 4;   // query-mask bytes [2][128]
   static constexpr int KF_OFF = QV_OFF + 2 * 128;       // [2] per-stage flag: some key of the block is masked / padding
   static constexpr int TOTAL = KF_OFF + 16 + 1024;
 };
@@ -109,10 +119,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* g_empty = bars + 31;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
   uint64_t* bias_full = bars + 33; // resident bias tiles of the current (h, query block) landed
   uint64_t* bias_empty = bars + 34;// ... and consumed by the last S MMA of that (h, query block)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
+  uint64_t* o_full = bars + 35;    // [2] O accumulator (slot it & 1) complete: committed behind the item's last P V
+  uint64_t* o_empty = bars + 37;   // [2] ... and read (with its row sums) by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 39);
   float* keyb = reinterpret_cast<float*>(smem + L::KB_OFF);   // [2][128]
   float* mxbuf = reinterpret_cast<float*>(smem + L::MX_OFF);  // [2][128]
-  float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][128]
+  float* lbuf = reinterpret_cast<float*>(smem + L::L_OFF);    // [2][2][128]
   uint8_t* qvbuf = smem + L::QV_OFF;                          // [2][128]
   uint32_t* kflag = reinterpret_cast<uint32_t*>(smem + L::KF_OFF);   // [2]
 
@@ -153,14 +165,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_empty[s], 4);
       mbar_init(&g_full[s], 1);
       mbar_init(&g_empty[s], 4);
       mbar_init(&s_full[s], 1);
       mbar_init(&kb_full[s], 1);
-      mbar_init(&kb_empty[s], 8);
+      mbar_init(&kb_empty[s], ATTN_SM_WARPS);
     }
-    mbar_init(&p_full[0], 8);
-    mbar_init(&p_full[1], 8);
+    mbar_init(&p_full[0], ATTN_SM_WARPS);
+    mbar_init(&p_full[1], ATTN_SM_WARPS);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -225,7 +239,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == ATTN_W_VPROD) {
     // ================================ V producer ==================================
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
@@ -311,23 +325,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
       mbar_wait(&v_full[g % nst], (g / nst) & 1);
+      const int it = g / nkv, j = g - it * nkv;
+      if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
-        const bool first = (g % nkv) == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A = P [128 rows x 16 keys] = 8 packed columns of the S / P buffer; B = V [key][dh], MN-major: 16 keys = 2 atoms
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
-          umma_bf16_ts(tmem_base + O_COL, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (!first || k != 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + O_COL + (it & 1) * 64, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (j != 0 || k != 0) ? 1u : 0u);
         }
         umma_commit(&v_empty[g % nst]);
         umma_commit(pv_done);
+        if (j == nkv - 1) umma_commit(&o_full[it & 1]);
       }
       __syncwarp();
       if (!s_issued) issue_s(g + 1);
     }
-  } else if (warp == 10) {
+  } else if (warp == ATTN_W_KEYMASK) {
     // ================================ key-mask warp ================================
     // stages, one block ahead of the softmax warps, the additive key term of every 128-key block:
     // 0 = usable key, -inf = masked key or tile padding beyond n (hides the mask's global-load latency)
@@ -362,21 +378,76 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) mbar_arrive(&kb_full[st]);
       }
     }
-  } else {
-    // ================================ softmax + epilogue (warps 2..9) ==============
+  } else if (warp >= ATTN_W_EPI) {
+    // ================================ epilogue warps ===============================
+    // O / l * gate -> out for one finished item while the softmax warps are already on the next one
     const int q = warp & 3;               // TMEM lane quarter
-    const int hk = (warp - 2) >> 2;       // which 64-key half of every 128-key block this thread owns
+    const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    for (int it = 0; it < my_items; ++it) {
+      int qb, h, b;
+      decode(it, qb, h, b);
+      const int slot = it & 1;
+      mbar_wait(&o_full[slot], (it >> 1) & 1);
+      tc_fence_after();
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATTN_NSPLIT; ++i) lsum += lbuf[(slot * ATTN_NSPLIT + i) * 128 + r];
+      const float inv_l = 1.0f / lsum;
+      mbar_wait(&g_full[slot], (it >> 1) & 1);
+      uint8_t* gt = smem + L::G_OFF + slot * L::Q_BYTES;
+#pragma unroll
+      for (int half = 0; half < DH / 32; ++half) {
+        uint32_t o[32];
+        tmem_ld32(tmem_base + O_COL + slot * 64 + half * 32 + lane_sel, o);
+        tmem_ld_wait();
+        if (half == DH / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[slot]);    // O and the row sums are in registers
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32); the gated output
+          // replaces the gate values it was computed from, in the same (swizzled) place
+          const uint32_t goff = (DH == 64) ? swz128_off(r, half * 4 + i) : (r * 64u + ((static_cast<uint32_t>(i) ^ ((r >> 1) & 3u)) << 4));
+          const uint4 gq = *reinterpret_cast<const uint4*>(gt + goff);
+          const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float a = __uint_as_float(o[8 * i + 2 * t]) * inv_l * bf16lo_to_f32(gw[t]);
+            const float bb = __uint_as_float(o[8 * i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
+            ow[t] = pack_bf16x2(a, bb);
+          }
+          *reinterpret_cast<uint4*>(gt + goff) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        // this warp's 32 rows of the tile; rows beyond n are clipped by the tensor map
+        tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();                        // the store has drained the tile: hand the slot back to the producer
+        mbar_arrive(&g_empty[slot]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ softmax warps ================================
+    constexpr int KPT = 128 / ATTN_NSPLIT;          // keys per thread and block
+    const int q = warp & 3;               // TMEM lane quarter
+    const int hk = (warp - 2) >> 2;       // which KPT-key slice of every 128-key block this thread owns
     const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const float NEG_INF = -__int_as_float(0x7f800000);
-    constexpr bool O_OWNER_ALL = (DH == 64);     // DH=64: each half owns 32 O columns; DH=32: half 0 owns all 32
-    const bool o_owner = O_OWNER_ALL || hk == 0;
-    const uint32_t o_col = O_COL + (O_OWNER_ALL ? hk * 32 : 0);
+    // lazy O rescaling (rare): the DH accumulator columns are shared out 16 per slice
+    const bool o_owner = hk * 16 < DH;
 
     for (int it = 0; it < my_items; ++it) {
-    int qb, h, b;
-    decode(it, qb, h, b);
     bool q_valid = true;
+    const uint32_t o_col = O_COL + (it & 1) * 64 + hk * 16;
 
     float m_run = NEG_INF, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
@@ -387,49 +458,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&s_full[st], (g >> 1) & 1);
       tc_fence_after();
 
-      float s[64];
+      // logits (log2 domain) = S (pair bias included by the tensor core) + keyterm
+      float s[KPT];
       {
-        uint32_t u0[32], u1[32];
-        tmem_ld32(tmem_base + S_COL + st * 128 + hk * 64 + lane_sel, u0);
-        tmem_ld32(tmem_base + S_COL + st * 128 + hk * 64 + 32 + lane_sel, u1);
+        uint32_t u[KPT];
+        tmem_ld32(tmem_base + S_COL + st * 128 + hk * KPT + lane_sel, u);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = __uint_as_float(u0[i]);
-          s[32 + i] = __uint_as_float(u1[i]);
-        }
+        for (int i = 0; i < KPT; ++i) s[i] = __uint_as_float(u[i]);
       }
-
-      // logits (log2 domain) = s (pair bias included by the tensor core) + keyterm
-      const float* kbs = keyb + st * 128 + hk * 64;
-      const bool keys_masked = kflag[st] != 0u;      // block-uniform: most blocks have every key usable
-      float mx0 = NEG_INF, mx1 = NEG_INF;
-      if (keys_masked) {
+      if (kflag[st] != 0u) {                 // block-uniform: most blocks have every key usable
+        const float* kbs = keyb + st * 128 + hk * KPT;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 k0 = *reinterpret_cast<const float4*>(kbs + c * 8);
-          const float4 k1 = *reinterpret_cast<const float4*>(kbs + c * 8 + 4);
-          s[c * 8 + 0] += k0.x; s[c * 8 + 1] += k0.y; s[c * 8 + 2] += k0.z; s[c * 8 + 3] += k0.w;
-          s[c * 8 + 4] += k1.x; s[c * 8 + 5] += k1.y; s[c * 8 + 6] += k1.z; s[c * 8 + 7] += k1.w;
+        for (int c = 0; c < KPT / 4; ++c) {
+          const float4 k4 = *reinterpret_cast<const float4*>(kbs + c * 4);
+          s[c * 4 + 0] += k4.x; s[c * 4 + 1] += k4.y; s[c * 4 + 2] += k4.z; s[c * 4 + 3] += k4.w;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&kb_empty[st]);
       if (!q_valid) {                        // rare: masked query row -> uniform over the n real keys
 #pragma unroll
-        for (int k = 0; k < 64; ++k) s[k] = (j * 128 + hk * 64 + k) < p.n ? 0.f : NEG_INF;
+        for (int k = 0; k < KPT; ++k) s[k] = (j * 128 + hk * KPT + k) < p.n ? 0.f : NEG_INF;
       }
+      float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-      for (int k = 0; k < 64; k += 2) {
-        mx0 = fmaxf(mx0, s[k]);
-        mx1 = fmaxf(mx1, s[k + 1]);
+      for (int k = 4; k < KPT; k += 4) {
+        mx0 = fmaxf(mx0, fmaxf(s[k], s[k + 1]));
+        mx1 = fmaxf(mx1, fmaxf(s[k + 2], s[k + 3]));
       }
-      mxbuf[hk * 128 + r] = fmaxf(mx0, mx1);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // only the two warps sharing these 32 rows
-      float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), mxbuf[(hk ^ 1) * 128 + r]));
+      // (double buffered by block parity: a warp can only be one named barrier ahead of the slowest reader)
+      float* mxb = mxbuf + st * ATTN_NSPLIT * 128;
+      mxb[hk * 128 + r] = fmaxf(mx0, mx1);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * ATTN_NSPLIT) : "memory");   // the warps sharing these 32 rows
+      float m_new = m_run;
+#pragma unroll
+      for (int i = 0; i < ATTN_NSPLIT; ++i) m_new = fmaxf(m_new, mxb[i * 128 + r]);
       // Lazy rescaling: the running maximum only has to be SOME upper bound up to a factor that neither overflows bf16 P nor
       // the fp32 sums.  While the block maximum exceeds it by <= 2^8 (log2 domain) we keep the stale one and skip the
-      // TMEM round trip of O; the decision is made per warp (both warps sharing these rows see identical values).
+      // TMEM round trip of O; the decision is made per warp (all warps sharing these rows see identical values).
       bool rescale = true;
       if (j > 0) {
         rescale = __any_sync(0xffffffffu, m_new > m_run + 8.0f);
@@ -438,12 +505,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
       const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
       float ls0 = 0.f, ls1 = 0.f;
+      uint32_t pk[KPT / 2];
 #pragma unroll
-      for (int k = 0; k < 64; k += 2) {
+      for (int k = 0; k < KPT; k += 2) {
         const float e0 = fast_exp2(s[k] - m_use);
         const float e1 = fast_exp2(s[k + 1] - m_use);
-        s[k] = e0; s[k + 1] = e1;
         ls0 += e0; ls1 += e1;
+        pk[k >> 1] = pack_bf16x2(e0, e1);
       }
       l_run = l_run * corr + (ls0 + ls1);
       m_run = m_new;
@@ -453,72 +521,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(pv_done, (g - 1) & 1);
         tc_fence_after();
         if (o_owner) {
-          uint32_t o[32];
-          tmem_ld32(tmem_base + o_col + lane_sel, o);
+          uint32_t o[16];
+          tmem_ld16(tmem_base + o_col + lane_sel, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-          tmem_st32(tmem_base + o_col + lane_sel, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          tmem_st16(tmem_base + o_col + lane_sel, o);
         }
       }
-      // P_j -> tensor memory: this thread's 64 keys become 32 packed columns [hk*32, hk*32+32) of the S buffer.  Those
-      // columns held logits of the hk = 0 half, which its owner loaded before the row-max barrier above.
-      {
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16x2(s[2 * c], s[2 * c + 1]);
-        tmem_st32(tmem_base + S_COL + st * 128 + hk * 32 + lane_sel, pk);
+      // P_j -> tensor memory: this thread's KPT keys become KPT/2 packed columns of the S buffer.  Those columns held logits
+      // of a lower slice, which its owner loaded before the row-max barrier above.
+      tmem_st16(tmem_base + S_COL + st * 128 + hk * (KPT / 2) + lane_sel, pk);
+      if (j == nkv - 1) {
+        // hand the item over: its row sums go to the epilogue warps (slot it & 1, free once they have read the item that
+        // used it before); the matching O follows through o_full, committed behind the P V this arrival triggers
+        mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);
+        lbuf[((it & 1) * ATTN_NSPLIT + hk) * 128 + r] = l_run;
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
-      // the previous item's output tile has had a whole key block of time to drain: hand its gate slot back to the producer
-      if (j == 0 && it > 0 && hk == 0 && lane == 0) {
-        tma_store_wait_read<0>();
-        mbar_arrive(&g_empty[(it - 1) & 1]);
-      }
-    }
-
-    // ---- epilogue: O / l * gate -> out ----
-    lbuf[hk * 128 + r] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float inv_l = 1.0f / (l_run + lbuf[(hk ^ 1) * 128 + r]);
-    mbar_wait(pv_done, (it * nkv + nkv - 1) & 1);
-    tc_fence_after();
-    mbar_wait(&g_full[it & 1], (it >> 1) & 1);
-    uint8_t* gt = smem + L::G_OFF + (it & 1) * L::Q_BYTES;
-    if (o_owner) {
-      uint32_t o[32];
-      tmem_ld32(tmem_base + o_col + lane_sel, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32); the gated output
-        // replaces the gate values it was computed from, in the same (swizzled) place
-        const uint32_t goff = (DH == 64) ? swz128_off(r, hk * 4 + i) : (r * 64u + ((static_cast<uint32_t>(i) ^ ((r >> 1) & 3u)) << 4));
-        const uint4 gq = *reinterpret_cast<const uint4*>(gt + goff);
-        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float a = __uint_as_float(o[8 * i + 2 * t]) * inv_l * bf16lo_to_f32(gw[t]);
-          const float bb = __uint_as_float(o[8 * i + 2 * t + 1]) * inv_l * bf16hi_to_f32(gw[t]);
-          ow[t] = pack_bf16x2(a, bb);
-        }
-        *reinterpret_cast<uint4*>(gt + goff) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-    }
-    tc_fence_before();            // O has been read: order it before the next item's first P V
-    fence_proxy_async_smem();
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both column halves of these 32 rows are in the tile
-    if (hk == 0 && lane == 0) {
-      // rows beyond n are clipped by the tensor map
-      tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
-      tma_store_commit();
     }
     }  // work items
-    if (hk == 0 && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last output store
   }
 
   tc_fence_before();
