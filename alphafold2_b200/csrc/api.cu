@@ -91,7 +91,8 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 // bf16 tensor map. dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
 int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
               const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz,
-              CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+              CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+              CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   auto fn = encode_fn();
   if (!fn) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -107,7 +108,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
   for (int i = 0; i + 1 < rank; ++i)
     if (gstr[i] & 15) return fail(AF2_ERR_BAD_ARG, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gstr[i]);
   CUresult r = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AF2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return AF2_OK;
@@ -431,11 +432,15 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   unsigned long long str[3] = {(unsigned long long)(tok_si * ld * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * ld * 2)};
   unsigned box[4] = {(unsigned)dh, 128, 1, 1};
   const CUtensorMapSwizzle swz = (dh == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz));
-  AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz));
-  AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz));
+  // A box row is ONE head's slice of a token (dh * 2 bytes); the bytes next to it belong to other heads, which other CTAs
+  // read at other times, so the L2 fill granularity must not exceed the row (256B promotion doubled the DRAM reads).
+  const CUtensorMapL2promotion promo = (dh == 64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz, bf, promo));
+  AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz, bf, promo));
+  AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz, bf, promo));
   unsigned long long gstr[3] = {(unsigned long long)(tok_si * I * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * I * 2)};
-  AF2_TRY(make_tmap(&tg, gate, 4, dims, gstr, box, swz));
+  AF2_TRY(make_tmap(&tg, gate, 4, dims, gstr, box, swz, bf, promo));
   unsigned obox[4] = {(unsigned)dh, 32, 1, 1};            // the output leaves per 32-row quarter of a query block
   AF2_TRY(make_tmap(&to, out, 4, dims, gstr, obox, swz));
   if (bias) {

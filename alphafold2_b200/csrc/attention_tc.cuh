@@ -133,16 +133,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nkv = (p.n + 127) / 128;
   const int nqb = nkv;
   const int total_items = nqb * p.heads * p.nbatch;
-  // item id = ((h * nqb + qb) * nbatch + b'); this CTA owns ids [item0, item0 + my_items)
-  const int item0 = static_cast<int>(static_cast<long long>(total_items) * blockIdx.x / gridDim.x);
-  const int my_items = static_cast<int>(static_cast<long long>(total_items) * (blockIdx.x + 1) / gridDim.x) - item0;
+  // Work split.  With two query blocks (n <= 256) CTAs 2c and 2c+1 walk the SAME contiguous range of (h, b') units, one per
+  // query block: they load the same K/V tiles at about the same time, so the second read hits L2 instead of HBM, and each
+  // keeps the bias tiles of its own (h, query block) resident.  Otherwise item id = ((h * nqb + qb) * nbatch + b') and this
+  // CTA owns the ids [item0, item0 + my_items).
+  const bool paired = (nqb == 2) && (gridDim.x % 2 == 0);
+  const int n_units = paired ? p.heads * p.nbatch : total_items;
+  const int n_owners = paired ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
+  const int owner = paired ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
+  const int item0 = static_cast<int>(static_cast<long long>(n_units) * owner / n_owners);
+  const int my_items = static_cast<int>(static_cast<long long>(n_units) * (owner + 1) / n_owners) - item0;
   auto decode = [&](int it, int& qb_, int& h_, int& b_) {
     const int id = item0 + it;
     b_ = id % p.nbatch;
-    qb_ = (id / p.nbatch) % nqb;
-    h_ = id / (p.nbatch * nqb);
+    if (paired) {
+      qb_ = static_cast<int>(blockIdx.x) & 1;
+      h_ = id / p.nbatch;
+    } else {
+      qb_ = (id / p.nbatch) % nqb;
+      h_ = id / (p.nbatch * nqb);
+    }
   };
-  auto combo_of = [&](int it) { return (item0 + it) / p.nbatch; };       // (h, query block) index: selects the bias tiles
+  auto combo_of = [&](int it) { return (item0 + it) / p.nbatch; };       // changes with (h, query block): selects the bias tiles
   const bool resident = p.has_bias && nkv <= 2;
   const int nst = p.has_bias ? 2 : 4;                                    // K/V pipeline depth
   const int stage_stride = (p.has_bias && !resident) ? L::STAGE_BYTES : L::KV_BYTES;
