@@ -13,6 +13,7 @@
 #include "../../include/af2b200.h"
 #include "attention_tc.cuh"
 #include "attention2_tc.cuh"
+#include "chan2tok_tma.cuh"
 #include "gemm_tc.cuh"
 #include "proj_tc.cuh"
 #include "simt_kernels.cuh"
@@ -114,6 +115,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
   return AF2_OK;
 }
 
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 // bump allocator over the caller's workspace
@@ -338,8 +340,47 @@ int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_b
   return AF2_OK;
 }
 
+template <int D>
+int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s) {
+  using L = Chan2TokSmem<D>;
+  static bool configured = false;
+  auto kern = chan_to_token_tma_kernel<D>;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  CUtensorMap tx, tg, ty;
+  {
+    unsigned long long dx[2] = {(unsigned long long)T, (unsigned long long)D};
+    unsigned long long sx[1] = {(unsigned long long)p.chan_stride * 4};
+    unsigned bx[2] = {C2T_TOK, (unsigned)D};
+    AF2_TRY(make_tmap(&tx, p.src, 2, dx, sx, bx, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+    unsigned long long dy[2] = {(unsigned long long)D, (unsigned long long)T};
+    unsigned long long sy[1] = {(unsigned long long)D * 2};
+    unsigned by[2] = {64, C2T_TOK};
+    AF2_TRY(make_tmap(&ty, p.y, 2, dy, sy, by, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (p.mode == 0) AF2_TRY(make_tmap(&tg, p.gate, 2, dy, sy, by, CU_TENSOR_MAP_SWIZZLE_128B));
+    else tg = ty;
+  }
+  Chan2TokParams q;
+  q.T = T; q.mode = p.mode; q.gamma = p.gamma; q.beta = p.beta; q.scale = p.scale; q.scale_const = p.scale_const; q.eps = p.eps;
+  const long long tiles = (T + C2T_TOK - 1) / C2T_TOK;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)T * D * (p.mode == 0 ? 8.0 : 6.0));
+  kern<<<grid, L::THREADS, L::TOTAL, s>>>(tx, tg, ty, q);
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
+}
+
+int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
+
 int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
   const long long T = (long long)p.rows * p.n;
+  if (g_c2t_tma && p.pitch == p.n && (p.d == 256 || p.d == 128) && (p.chan_stride % 4) == 0 && T > 0 && T < (1ll << 31) &&
+      aligned16(p.src) && aligned16(p.y) && (p.mode != 0 || aligned16(p.gate))) {
+    // dense token grid: persistent TMA-pipelined kernel
+    return p.d == 256 ? launch_chan_to_token_tma<256>(p, T, s) : launch_chan_to_token_tma<128>(p, T, s);
+  }
   if (p.pitch == p.n && p.d % 64 == 0 && p.d <= 256 && (T % 4) == 0) {
     // dense token grid: 64-token tiles, fully coalesced
     const size_t smem = (size_t)p.d * 64 * sizeof(float) + 8 * 64 * 2 * sizeof(float);
@@ -511,6 +552,7 @@ void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : 
 int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
   if (const char* e = getenv("AF2_ATTN_VER")) g_attn_ver = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("AF2_C2T_TMA")) g_c2t_tma = atoi(e) != 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;

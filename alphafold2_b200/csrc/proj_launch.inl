@@ -20,7 +20,6 @@ int g_proj_ctas = 2;
 
 // can this LN -> Linear cluster run on the fused kernel?
 bool proj_dim_ok(int d) { return d % 64 == 0 && d >= 128 && d <= 256; }
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int CTAS, int KINDS>
 int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtensorMap& tx, ProjParams& p,

@@ -86,7 +86,7 @@ def test_axial_attention_fused(mode, d, H, dh, N, row):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("d,N,mix", [(256, 72, "outgoing"), (128, 136, "ingoing"), (256, 128, "ingoing")])
+@pytest.mark.parametrize("d,N,mix", [(256, 72, "outgoing"), (128, 136, "ingoing"), (256, 128, "ingoing"), (256, 70, "outgoing")])
 def test_triangle_multiply_fused(mode, d, N, mix):
     import alphafold2_b200 as A
     tm = A.TriangleMultiplicativeModule(dim=d, mix=mix)
@@ -104,7 +104,7 @@ def test_triangle_multiply_fused(mode, d, N, mix):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("d,N,S", [(256, 72, 9), (128, 64, 33)])
+@pytest.mark.parametrize("d,N,S", [(256, 72, 9), (128, 64, 33), (256, 50, 5)])
 def test_outer_mean_fused(mode, d, N, S):
     import alphafold2_b200 as A
     om = A.OuterMean(dim=d)
