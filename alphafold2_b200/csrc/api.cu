@@ -553,6 +553,7 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
   if (const char* e = getenv("AF2_ATTN_VER")) g_attn_ver = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("AF2_C2T_TMA")) g_c2t_tma = atoi(e) != 0;
+  if (const char* e = getenv("AF2_PROJ_PRODTILES")) g_proj_prod_tiles = atof(e);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;

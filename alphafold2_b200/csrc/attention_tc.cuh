@@ -516,15 +516,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
       const float corr = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
-      float ls0 = 0.f, ls1 = 0.f;
+      // packed fp32 pairs: one FADD2 subtracts the maximum from two logits, one FADD2 accumulates two terms of the row sum
+      const f32x2 nm2 = pack2(-m_use, -m_use);
+      f32x2 lsa = pack2(0.f, 0.f), lsb = pack2(0.f, 0.f);
       uint32_t pk[KPT / 2];
 #pragma unroll
-      for (int k = 0; k < KPT; k += 2) {
-        const float e0 = fast_exp2(s[k] - m_use);
-        const float e1 = fast_exp2(s[k + 1] - m_use);
-        ls0 += e0; ls1 += e1;
+      for (int k = 0; k < KPT; k += 4) {
+        float a0, a1, b0, b1;
+        unpack2(add2(pack2(s[k], s[k + 1]), nm2), a0, a1);
+        unpack2(add2(pack2(s[k + 2], s[k + 3]), nm2), b0, b1);
+        const float e0 = fast_exp2(a0), e1 = fast_exp2(a1), e2 = fast_exp2(b0), e3 = fast_exp2(b1);
+        lsa = add2(lsa, pack2(e0, e1));
+        lsb = add2(lsb, pack2(e2, e3));
         pk[k >> 1] = pack_bf16x2(e0, e1);
+        pk[(k >> 1) + 1] = pack_bf16x2(e2, e3);
       }
+      float ls0, ls1;
+      unpack2(add2(lsa, lsb), ls0, ls1);
       l_run = l_run * corr + (ls0 + ls1);
       m_run = m_new;
 

@@ -174,6 +174,57 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 
 // ------------------------------------------------------------------------------------------
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): two IEEE fp32 operations per instruction and lane; the
+// halves round exactly like the scalar instructions
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_fast / sigmoidf_fast on a pair: the polynomial, the +1 and the products run as packed instructions, only the clamp
+// and the two MUFU operations stay scalar (6 instead of 11 instructions per element).  The clamp acts on x^2 (<= 49):
+// beyond |x| = 7 the exponent is -5.3 x, which saturates to the exact limits 0 and x.
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+  float a, b;
+  unpack2(mul2(x, x), a, b);
+  const f32x2 x2 = pack2(fminf(a, 49.0f), fminf(b, 49.0f));
+  f32x2 q = fma2(x2, pack2(0.0009112266168574351f, 0.0009112266168574351f), pack2(-0.10617732324431346f, -0.10617732324431346f));
+  q = fma2(x2, q, pack2(-2.3017271259199106f, -2.3017271259199106f));
+  unpack2(mul2(x, q), a, b);
+  float ra, rb;
+  unpack2(add2(pack2(fast_exp2(a), fast_exp2(b)), pack2(1.0f, 1.0f)), a, b);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(b));
+  return mul2(x, pack2(ra, rb));
+}
+__device__ __forceinline__ f32x2 sigmoidf_fast2(f32x2 x) {
+  float a, b, ra, rb;
+  unpack2(mul2(x, pack2(-1.4426950408889634f, -1.4426950408889634f)), a, b);
+  unpack2(add2(pack2(fast_exp2(a), fast_exp2(b)), pack2(1.0f, 1.0f)), a, b);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(b));
+  return pack2(ra, rb);
+}
+
+// ------------------------------------------------------------------------------------------
 // TMEM allocation (one warp, .sync.aligned)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

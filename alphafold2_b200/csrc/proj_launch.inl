@@ -17,6 +17,7 @@ struct ProjCall {
 
 // 2: CTA-pair kernel (default); 1: single-CTA variant; 0: fused kernel disabled (legacy LayerNorm + GEMM launches)
 int g_proj_ctas = 2;
+double g_proj_prod_tiles = 4.0;   // cost of producing one A tile in units of one 256-column MMA tile (AF2_PROJ_PRODTILES)
 
 // can this LN -> Linear cluster run on the fused kernel?
 bool proj_dim_ok(int d) { return d % 64 == 0 && d >= 128 && d <= 256; }
@@ -49,7 +50,7 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   if (m_units <= 0) return AF2_OK;
   // column split: an item costs max(MMA time of its tiles, A-producer time) because A is double buffered; the producer
   // costs about as much as PROD_TILES column tiles, so splitting columns only pays when there are too few row units
-  const double PROD_TILES = 4.0;
+  const double PROD_TILES = g_proj_prod_tiles;
   int best = 1; double best_cost = 1e30;
   for (int ns = 1; ns <= p.n_tiles_total && ns <= 8; ++ns) {
     const long long items = (long long)m_units * ns;

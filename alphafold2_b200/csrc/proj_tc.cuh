@@ -94,24 +94,22 @@ __device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {
 template <int EK>
 __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t* g, float rs, uint32_t (&pk)[16]) {
   constexpr int mode = EpiTraits<EK>::mode, act = EpiTraits<EK>::act;
-  float v[32];
+  const f32x2 rs2 = pack2(rs, rs);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a;
+  for (int j = 0; j < 16; ++j) {
+    f32x2 a = pack2(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
     if constexpr (mode == EPI_GATED_BF16) {
-      const float gg = __uint_as_float(g[j]);
-      if constexpr (act == ACT_GELU) a = gelu_fast(gg);
-      else a = sigmoidf_fast(gg);
-      a *= __uint_as_float(u[j]);
+      const f32x2 gg = pack2(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
+      if constexpr (act == ACT_GELU) a = mul2(a, gelu_fast2(gg));
+      else a = mul2(a, sigmoidf_fast2(gg));
     } else {
-      a = __uint_as_float(u[j]);
-      if constexpr (act == ACT_SIGMOID) a = sigmoidf_fast(a);
+      if constexpr (act == ACT_SIGMOID) a = sigmoidf_fast2(a);
     }
-    if constexpr (EpiTraits<EK>::rowscale) a *= rs;
-    v[j] = a;
+    if constexpr (EpiTraits<EK>::rowscale) a = mul2(a, rs2);
+    float lo, hi;
+    unpack2(a, lo, hi);
+    pk[j] = pack_bf16x2(lo, hi);
   }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -200,32 +198,53 @@ __device__ __forceinline__ void proj_load_quad(RowQuad& b, const float4* xr, boo
 
 template <int NJ>
 __device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abuf, int r, bool live, float inv_d, float eps, int sub) {
-  float s = 0.f;
+  // all vector math on packed fp32 pairs (FADD2 / FFMA2): the producer warps are bound by instruction latency, not by memory
+  f32x2 lo[NJ], hi[NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) s += (b.v[j].x + b.v[j].y) + (b.v[j].z + b.v[j].w);
+  for (int j = 0; j < NJ; ++j) {
+    lo[j] = pack2(b.v[j].x, b.v[j].y);
+    hi[j] = pack2(b.v[j].z, b.v[j].w);
+  }
+  f32x2 sa = lo[0], sb = hi[0];
+#pragma unroll
+  for (int j = 1; j < NJ; ++j) {
+    sa = add2(sa, lo[j]);
+    sb = add2(sb, hi[j]);
+  }
+  float s0, s1;
+  unpack2(add2(sa, sb), s0, s1);
+  float s = s0 + s1;
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   const float mean = s * inv_d;
-  float sq = 0.f;
+  const f32x2 nm = pack2(-mean, -mean);
+  f32x2 qa = pack2(0.f, 0.f), qb = pack2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const float a = b.v[j].x - mean, bb = b.v[j].y - mean, cc = b.v[j].z - mean, dd = b.v[j].w - mean;
-    sq += a * a + bb * bb + cc * cc + dd * dd;
+    const f32x2 da = add2(lo[j], nm), db = add2(hi[j], nm);
+    qa = fma2(da, da, qa);
+    qb = fma2(db, db, qb);
   }
+  float q0, q1;
+  unpack2(add2(qa, qb), q0, q1);
+  float sq = q0 + q1;
   sq += __shfl_xor_sync(0xffffffffu, sq, 1);
   sq += __shfl_xor_sync(0xffffffffu, sq, 2);
   sq += __shfl_xor_sync(0xffffffffu, sq, 4);
   const float rs = live ? rsqrtf(sq * inv_d + eps) : 0.f;      // dead rows (beyond T) become zeros
   const float sh = -mean * rs;
+  const f32x2 rs2 = pack2(rs, rs), sh2 = pack2(sh, sh);
   // float4 chunk idx = j*8 + sub covers columns 4*idx..: k-block idx/16 = j/2, 16-byte chunk (idx%16)/2, half idx&1
   uint8_t* rowp = abuf + r * 128;
   const uint32_t sw = static_cast<uint32_t>(r & 7);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const uint32_t chunk = static_cast<uint32_t>(((j & 1) * 8 + sub) >> 1);
-    const uint2 o = make_uint2(pack_bf16x2(fmaf(b.v[j].x, rs, sh), fmaf(b.v[j].y, rs, sh)),
-                               pack_bf16x2(fmaf(b.v[j].z, rs, sh), fmaf(b.v[j].w, rs, sh)));
+    float o0, o1, o2, o3;
+    unpack2(fma2(lo[j], rs2, sh2), o0, o1);
+    unpack2(fma2(hi[j], rs2, sh2), o2, o3);
+    const uint2 o = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
     *reinterpret_cast<uint2*>(rowp + (j >> 1) * 16384 + ((chunk ^ sw) << 4) + (sub & 1) * 8) = o;
   }
 }
