@@ -12,7 +12,6 @@
 
 #include "../../include/af2b200.h"
 #include "attention_tc.cuh"
-#include "attention2_tc.cuh"
 #include "chan2tok_tma.cuh"
 #include "gemm_tc.cuh"
 #include "proj_tc.cuh"
@@ -417,33 +416,9 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
 // -------------------------------------------------------------------------------------------------
 // attention launch (one folded batch group)
 // -------------------------------------------------------------------------------------------------
-int g_attn_ver = 1;   // 1: attention_tc.cuh (default); 2: experimental split-KV / P-in-TMEM kernel attention2_tc.cuh (AF2_ATTN_VER=2)
-
-template <int DH>
-int launch_attention2_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
-                           const CUtensorMap& tg, const AttnParams& p, cudaStream_t s) {
-  using L = Attn2Smem<DH>;
-  static bool configured = false;
-  auto kern = attention2_tc_kernel<DH>;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
-  const long long items = (long long)((p.n + 127) / 128) * p.heads * p.nbatch;
-  if (items <= 0) return AF2_OK;
-  const int grid = (int)(items < sm_count() ? items : sm_count());     // persistent CTAs
-  const double tokens = (double)p.n * p.nbatch;
-  ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
-               tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
-  kern<<<grid, ATTN2_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, p);
-  CUDA_OK(cudaGetLastError());
-  return AF2_OK;
-}
-
 template <int DH>
 int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
                           const CUtensorMap& tg, const CUtensorMap& to, const AttnParams& p, cudaStream_t s) {
-  if (g_attn_ver == 2) return launch_attention2_inst<DH>(tq, tk, tv, tbias, tg, p, s);
   using L = AttnSmem<DH>;
   static bool configured = false;
   auto kern = attention_tc_kernel<DH>;
@@ -551,7 +526,6 @@ void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : 
 
 int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
-  if (const char* e = getenv("AF2_ATTN_VER")) g_attn_ver = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("AF2_C2T_TMA")) g_c2t_tma = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_PRODTILES")) g_proj_prod_tiles = atof(e);
   int dev = 0;
