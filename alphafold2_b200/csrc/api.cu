@@ -416,6 +416,8 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
 // -------------------------------------------------------------------------------------------------
 // attention launch (one folded batch group)
 // -------------------------------------------------------------------------------------------------
+int g_attn_kdepth = 3;   // K ring depth of the resident-bias attention mode (AF2_ATTN_KDEPTH=2|3)
+
 template <int DH>
 int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
                           const CUtensorMap& tg, const CUtensorMap& to, const AttnParams& p, cudaStream_t s) {
@@ -472,6 +474,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.n = n; p.heads = heads; p.nbatch = nbatch; p.has_bias = bias != nullptr;
   p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
   p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
+  p.k_depth = g_attn_kdepth;
   if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
   if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
@@ -528,6 +531,8 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_CTAS")) af2_set_proj_mode(atoi(e));
   if (const char* e = getenv("AF2_C2T_TMA")) g_c2t_tma = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_PRODTILES")) g_proj_prod_tiles = atof(e);
+  if (const char* e = getenv("AF2_PROJ_BALANCE")) g_proj_balance = atoi(e) != 0;
+  if (const char* e = getenv("AF2_ATTN_KDEPTH")) g_attn_kdepth = atoi(e) == 2 ? 2 : 3;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;

@@ -17,6 +17,7 @@ struct ProjCall {
 
 // 2: CTA-pair kernel (default); 1: single-CTA variant; 0: fused kernel disabled (legacy LayerNorm + GEMM launches)
 int g_proj_ctas = 2;
+int g_proj_balance = 1;           // 1: equal (row unit, column tile) ranges per cluster; 0: round-robin items (AF2_PROJ_BALANCE)
 double g_proj_prod_tiles = 4.0;   // cost of producing one A tile in units of one 256-column MMA tile (AF2_PROJ_PRODTILES)
 
 // can this LN -> Linear cluster run on the fused kernel?
@@ -60,7 +61,8 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
   p.nsplit = best;
-  const long long items = (long long)m_units * p.nsplit;
+  p.balance = g_proj_balance;
+  const long long items = p.balance ? (long long)m_units * p.n_tiles_total : (long long)m_units * p.nsplit;
   const int clusters = (int)(items < max_clusters ? items : max_clusters);
   ProfScope ps(s, KC_GEMM_LINEAR, flops, bytes);
   cudaLaunchConfig_t cfg;

@@ -61,7 +61,8 @@ struct ProjParams {
   int nseg;
   ProjSeg seg[PROJ_MAX_SEG];
   int n_tiles_total;
-  int nsplit;                    // column chunks per row unit
+  int nsplit;                    // column chunks per row unit (balance == 0)
+  int balance;                   // 1: every cluster owns a contiguous range of the flat (row unit, column tile) sequence
   int m_tiles;                   // ceil(T / 128)
 };
 
@@ -368,14 +369,27 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 
   // ---- work decomposition: item = (row unit of 128*CTAS rows, column chunk) ----
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
+  // balance == 0: items (row unit, column chunk) are dealt round-robin; a cluster's load is a whole number of items.
+  // balance == 1: the flat sequence of (row unit, column tile) pairs is cut into nclusters equal ranges; a range becomes a
+  //               partial first unit, whole units and a partial last unit.  Every cluster then runs the same number of
+  //               tiles (+-1) at the price of producing at most one extra A tile.
+  const int ntt = p.n_tiles_total;
+  const long long flat = static_cast<long long>(m_units) * ntt;
+  const long long f0 = flat * cluster_id / nclusters, f1 = flat * (cluster_id + 1) / nclusters;
   const int total_items = m_units * p.nsplit;
-  const int tiles_per_chunk = (p.n_tiles_total + p.nsplit - 1) / p.nsplit;
-  const int my_items = (total_items > cluster_id) ? (total_items - 1 - cluster_id) / nclusters + 1 : 0;
+  const int tiles_per_chunk = (ntt + p.nsplit - 1) / p.nsplit;
+  const int my_items = p.balance ? (f1 > f0 ? static_cast<int>((f1 - 1) / ntt - f0 / ntt) + 1 : 0)
+                                 : ((total_items > cluster_id) ? (total_items - 1 - cluster_id) / nclusters + 1 : 0);
   const int nkb = p.d / GEMM_BK;
-  auto item_unit = [&](int it) { return (cluster_id + it * nclusters) / p.nsplit; };
-  auto item_chunk = [&](int it) { return (cluster_id + it * nclusters) % p.nsplit; };
-  auto chunk_t0 = [&](int ch) { return ch * tiles_per_chunk; };
-  auto chunk_t1 = [&](int ch) { return min((ch + 1) * tiles_per_chunk, p.n_tiles_total); };
+  auto item_unit = [&](int it) { return p.balance ? static_cast<int>(f0 / ntt) + it : (cluster_id + it * nclusters) / p.nsplit; };
+  auto item_t0 = [&](int it) {
+    if (p.balance) return it == 0 ? static_cast<int>(f0 % ntt) : 0;
+    return ((cluster_id + it * nclusters) % p.nsplit) * tiles_per_chunk;
+  };
+  auto item_t1 = [&](int it) {
+    if (p.balance) return it == my_items - 1 ? static_cast<int>((f1 - 1) % ntt) + 1 : ntt;
+    return min(((cluster_id + it * nclusters) % p.nsplit + 1) * tiles_per_chunk, ntt);
+  };
   auto seg_of = [&](int nt) {
     int s = 0;
 #pragma unroll
@@ -393,8 +407,8 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_items; ++it) {
-        const int ch = item_chunk(it);
-        for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt) {
+        const int t1 = item_t1(it);
+        for (int nt = item_t0(it); nt < t1; ++nt) {
           for (int kb = -1; kb < nkb; ++kb) {                 // kb = -1: the tile's bias block (rows x 16 bf16)
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sb = smem + L::B_OFF + stage * L::B_STAGE;
@@ -422,12 +436,11 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       uint32_t tcnt = 0;
       for (int it = 0; it < my_items; ++it) {
         const int ab = it & 1;
-        const int ch = item_chunk(it);
         mbar_wait(&afull_bar[ab], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t sa0 = smem_u32(smem + L::A_OFF + ab * PROJ_A_BUF);
-        const int t1 = chunk_t1(ch);
-        for (int nt = chunk_t0(ch); nt < t1; ++nt, ++tcnt) {
+        const int t1 = item_t1(it);
+        for (int nt = item_t0(it); nt < t1; ++nt, ++tcnt) {
           const int acc = tcnt & 1;
           mbar_wait(&tempty_bar[acc], ((tcnt >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -484,12 +497,12 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ec = 0, gc = 0, tcnt = 0;
     for (int it = 0; it < my_items; ++it) {
-      const int unit = item_unit(it), ch = item_chunk(it);
+      const int unit = item_unit(it), t1 = item_t1(it);
       const int m0w = (unit * CTAS + static_cast<int>(rank)) * 128 + q * 32;
       const long long row = static_cast<long long>(m0w) + lane;
       float rs = 1.0f;
       if (p.rowmask && row < p.T) rs = p.rowmask[row] ? 1.0f : 0.0f;
-      for (int nt = chunk_t0(ch); nt < chunk_t1(ch); ++nt, ++tcnt) {
+      for (int nt = item_t0(it); nt < t1; ++nt, ++tcnt) {
         const ProjSeg& sg = p.seg[seg_of(nt)];
         const int acc = tcnt & 1;
         const int W = proj_tile_width(sg.kind);
