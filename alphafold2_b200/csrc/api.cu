@@ -416,8 +416,6 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
 // -------------------------------------------------------------------------------------------------
 // attention launch (one folded batch group)
 // -------------------------------------------------------------------------------------------------
-int g_attn_kdepth = 3;   // K ring depth of the resident-bias attention mode (AF2_ATTN_KDEPTH=2|3)
-
 template <int DH>
 int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
                           const CUtensorMap& tg, const CUtensorMap& to, const AttnParams& p, cudaStream_t s) {
@@ -474,7 +472,6 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.n = n; p.heads = heads; p.nbatch = nbatch; p.has_bias = bias != nullptr;
   p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
   p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
-  p.k_depth = g_attn_kdepth;
   if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
   if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
@@ -525,6 +522,14 @@ long long af2_profile_read(int cls, double* ms, double* flops, double* bytes) {
   return n;
 }
 
+// debug: copies the clock64 stamps of the last fused-projection launch (AF2_PROJ_TRACE=1) to `out` (2048 entries)
+int af2_debug_proj_trace(long long* out) {
+  if (!g_proj_trace) return fail(AF2_ERR_BAD_ARG, "projection trace not enabled (AF2_PROJ_TRACE=1)");
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, g_proj_trace, 2048 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return AF2_OK;
+}
+
 void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : ctas); }
 
 int af2_check_device(void) {
@@ -532,7 +537,13 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_C2T_TMA")) g_c2t_tma = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_PRODTILES")) g_proj_prod_tiles = atof(e);
   if (const char* e = getenv("AF2_PROJ_BALANCE")) g_proj_balance = atoi(e) != 0;
-  if (const char* e = getenv("AF2_ATTN_KDEPTH")) g_attn_kdepth = atoi(e) == 2 ? 2 : 3;
+  if (const char* e = getenv("AF2_PROJ_WIDE")) g_proj_wide = atoi(e) != 0;
+  if (const char* e = getenv("AF2_PROJ_TRACE")) {
+    if (atoi(e) != 0 && !g_proj_trace) {
+      if (cudaMalloc(&g_proj_trace, 2048 * sizeof(long long)) != cudaSuccess) g_proj_trace = nullptr;
+      else cudaMemset(g_proj_trace, 0, 2048 * sizeof(long long));
+    }
+  }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(AF2_ERR_CUDA, "no CUDA device");
   int major = 0;

@@ -47,7 +47,6 @@ struct AttnParams {
   __nv_bfloat16* out;         // [token, heads*DH]
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
-  int k_depth;        // K ring depth in the resident-bias mode (2 or 3)
 };
 
 constexpr int ATTN_NSPLIT = 4;                      // softmax threads per query row (each owns 128 / NSPLIT keys of a block)
@@ -72,24 +71,20 @@ struct AttnSmem {
   static constexpr int IDENT_BYTES = 32 * 256;
   static constexpr int Q_OFF = 0;                       // [2] Q tiles (slot it & 1)
   static constexpr int G_OFF = 2 * Q_BYTES;             // [2] sigmoid-gate tiles [128 q x DH] (same layout as Q)
-  // K/V (+ bias) region, carved at run time:
-  //   resident bias (n <= 256): K x 3 | V x 2 | bias tiles of key blocks 0, 1     (K's ring is one deeper than V's: a K slot
-  //                             refills when the block's S retires, and S(g+1) must be done before softmax(g) ends)
+  // K/V (+ bias) region of 2 * STAGE_BYTES, carved at run time:
+  //   resident bias (n <= 256): [K V] x 2 stages | bias tiles of key blocks 0, 1
   //   streamed bias (n > 256) : [K V bias] x 2 stages
   //   no bias                 : [K V] x 4 stages
   static constexpr int KV_BYTES = K_BYTES + V_BYTES;
   static constexpr int STAGE_OFF = 4 * Q_BYTES;
-  static constexpr int REGION_BYTES = 3 * K_BYTES + 2 * V_BYTES + 2 * BIAS_BYTES;
-  static_assert(REGION_BYTES >= 2 * STAGE_BYTES && REGION_BYTES >= 4 * KV_BYTES, "K/V region too small for the other modes");
-  static constexpr int IDENT_OFF = STAGE_OFF + REGION_BYTES;
+  static constexpr int IDENT_OFF = STAGE_OFF + 2 * STAGE_BYTES;
   static constexpr int BAR_OFF = IDENT_OFF + IDENT_BYTES;
   static constexpr int KB_OFF = BAR_OFF + 384;          // float key term (0 / -inf) [2][128]
   static constexpr int MX_OFF = KB_OFF + 2 * 128 * 4;   // float row-max exchange [2 block parities][NSPLIT][128]
   static constexpr int L_OFF = MX_OFF + 2 * ATTN_NSPLIT * 128 * 4;   // float row sums handed to the epilogue warps [2 slots][NSPLIT][128]
   static constexpr int QV_OFF = L_OFF + 2 * ATTN_NSPLIT * 128 * 4;   // query-mask bytes [2][128]
   static constexpr int KF_OFF = QV_OFF + 2 * 128;       // [2] per-stage flag: some key of the block is masked / padding
-  static constexpr int TOTAL = KF_OFF + 16;
-  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can use");
+  static constexpr int TOTAL = KF_OFF + 16 + 1024;
 };
 
 // tmQ/tmK/tmV: 4-D maps over the projection buffer, dims (e [DH], i [n], h [heads], b' [nbatch]),
@@ -161,14 +156,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   };
   auto combo_of = [&](int it) { return (item0 + it) / p.nbatch; };       // changes with (h, query block): selects the bias tiles
   const bool resident = p.has_bias && nkv <= 2;
-  const int nk = resident ? (p.k_depth == 2 ? 2 : 3) : (p.has_bias ? 2 : 4);   // K ring depth
-  const int nv = p.has_bias ? 2 : 4;                                     // V ring depth
+  const int nst = p.has_bias ? 2 : 4;                                    // K/V pipeline depth
   const int stage_stride = (p.has_bias && !resident) ? L::STAGE_BYTES : L::KV_BYTES;
-  auto k_off = [&](int g) { return L::STAGE_OFF + (resident ? (g % nk) * L::K_BYTES : (g % nk) * stage_stride); };
-  auto v_off = [&](int g) {
-    return L::STAGE_OFF + (resident ? 3 * L::K_BYTES + (g % nv) * L::V_BYTES : (g % nv) * stage_stride + L::K_BYTES);
-  };
-  const int bias_res_off = L::STAGE_OFF + 3 * L::K_BYTES + 2 * L::V_BYTES;   // resident tiles: + j * BIAS_BYTES
+  const int bias_res_off = L::STAGE_OFF + 2 * L::KV_BYTES;               // resident tiles: + j * BIAS_BYTES
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0, O_COL = 256;
 
@@ -247,10 +237,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool stream_bias = p.has_bias && !resident;
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
-          const int kst = g % nk;
+          const int kst = g % nst;
           // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
-          mbar_wait(&k_empty[kst], ((g / nk) & 1) ^ 1);
-          uint8_t* sk = smem + k_off(g);
+          mbar_wait(&k_empty[kst], ((g / nst) & 1) ^ 1);
+          uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
           mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
           tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
           if (stream_bias) {
@@ -269,10 +259,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         decode(it, qb, h, b);
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
-          const int vst = g % nv;
-          mbar_wait(&v_empty[vst], ((g / nv) & 1) ^ 1);
-          mbar_arrive_expect_tx(&v_full[vst], L::V_BYTES);
-          tma_load_4d(smem + v_off(g), &tmV, &v_full[vst], 0, j * 128, h, b);
+          const int kst = g % nst;
+          mbar_wait(&v_empty[kst], ((g / nst) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
+          tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
         }
       }
     }
@@ -285,7 +275,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int prev_combo = -1, nc = 0;
     auto issue_s = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
-      const int st = g & 1, kst = g % nk;
+      const int st = g & 1, kst = g % nst;
       if (j == 0) {
         mbar_wait(&q_full[it & 1], (it >> 1) & 1);
         if (resident && combo_of(it) != prev_combo) {     // this CTA's range entered the next (h, query block): new bias tiles
@@ -294,11 +284,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ++nc;
         }
       }
-      mbar_wait(&k_full[kst], (g / nk) & 1);
+      mbar_wait(&k_full[kst], (g / nst) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF + (it & 1) * L::Q_BYTES);
-        const uint32_t sk = smem_u32(smem + k_off(g));
+        const uint32_t sk = smem_u32(smem + L::STAGE_OFF + kst * stage_stride);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
           const uint64_t ad = umma_smem_desc(sq + k * 32, 16, SBO, SWZ);
@@ -336,7 +326,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (!mbar_test(&q_full[it & 1], (it >> 1) & 1)) return false;
         if (resident && combo_of(it) != prev_combo && !mbar_test(bias_full, nc & 1)) return false;
       }
-      return mbar_test(&k_full[g % nk], (g / nk) & 1);
+      return mbar_test(&k_full[g % nst], (g / nst) & 1);
     };
     if (total_blocks > 0) issue_s(0);
     for (int g = 0; g < total_blocks; ++g) {
@@ -346,19 +336,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
-      mbar_wait(&v_full[g % nv], (g / nv) & 1);
+      mbar_wait(&v_full[g % nst], (g / nst) & 1);
       const int it = g / nkv, j = g - it * nkv;
       if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sv = smem_u32(smem + v_off(g));
+        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A = P [128 rows x 16 keys] = 8 packed columns of the S / P buffer; B = V [key][dh], MN-major: 16 keys = 2 atoms
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
           umma_bf16_ts(tmem_base + O_COL + (it & 1) * 64, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (j != 0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[g % nv]);
+        umma_commit(&v_empty[g % nst]);
         umma_commit(pv_done);
         if (j == nkv - 1) umma_commit(&o_full[it & 1]);
       }

@@ -17,7 +17,9 @@ struct ProjCall {
 
 // 2: CTA-pair kernel (default); 1: single-CTA variant; 0: fused kernel disabled (legacy LayerNorm + GEMM launches)
 int g_proj_ctas = 2;
+int g_proj_wide = 1;              // 1: 64-column epilogue steps where the segment width allows (AF2_PROJ_WIDE)
 int g_proj_balance = 1;           // 1: equal (row unit, column tile) ranges per cluster; 0: round-robin items (AF2_PROJ_BALANCE)
+long long* g_proj_trace = nullptr; // device buffer of 1024 stamps when AF2_PROJ_TRACE=1 (debug only)
 double g_proj_prod_tiles = 4.0;   // cost of producing one A tile in units of one 256-column MMA tile (AF2_PROJ_PRODTILES)
 
 // can this LN -> Linear cluster run on the fused kernel?
@@ -62,6 +64,7 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   }
   p.nsplit = best;
   p.balance = g_proj_balance;
+  p.trace = g_proj_trace;
   const long long items = p.balance ? (long long)m_units * p.n_tiles_total : (long long)m_units * p.nsplit;
   const int clusters = (int)(items < max_clusters ? items : max_clusters);
   ProfScope ps(s, KC_GEMM_LINEAR, flops, bytes);
@@ -95,16 +98,19 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
     kinds |= KBIT(o.kind);
     const bool chan = (o.kind == EK_STORE_CH || o.kind == EK_STORE_CH_SIG || o.kind == EK_GATED_CH_SIG);
     if (!aligned16(o.out) || (o.ld * 2) % 16) return fail(AF2_ERR_BAD_ARG, "proj: output %d not TMA-describable", i);
-    // every epilogue warp stores 32 x 32 element boxes (64-byte rows, 64B swizzle) from its private staging buffer
+    // every epilogue warp stores from its private 4 KB staging block: 64 columns x 32 rows per store when the segment's
+    // width allows it (128-byte rows, 128B swizzle; channel-major: 64 channels x 32 tokens, 64B swizzle), else 32 x 32
+    const bool wide = g_proj_wide && (o.out_cols % 64) == 0;
+    p.seg[i].wide = wide ? 1 : 0;
     if (!chan) {
       unsigned long long dc[3] = {(unsigned long long)o.out_cols, (unsigned long long)c.T, 1ull};
       unsigned long long sc[2] = {(unsigned long long)o.ld * 2, (unsigned long long)o.ld * c.T * 2};
-      unsigned bc[3] = {32, 32, 1};
-      AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B));
+      unsigned bc[3] = {wide ? 64u : 32u, 32, 1};
+      AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
     } else {
       unsigned long long dc[3] = {(unsigned long long)c.T, (unsigned long long)o.out_cols, 1ull};
       unsigned long long sc[2] = {(unsigned long long)o.ld * 2, (unsigned long long)o.ld * o.out_cols * 2};
-      unsigned bc[3] = {32, 32, 1};
+      unsigned bc[3] = {32, wide ? 64u : 32u, 1};
       AF2_TRY(make_tmap(&tc[i], o.out, 3, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B));
     }
     const int W = (o.kind == EK_GATED_TOK_GELU || o.kind == EK_GATED_CH_SIG) ? 2 : 1;

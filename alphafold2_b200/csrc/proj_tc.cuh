@@ -48,7 +48,7 @@ struct ProjSeg {
   int kind;              // EpiKind
   int out_cols;          // valid output columns of the segment
   int map;               // output tensor map index (0..2)
-  int pad;
+  int wide;              // 1: out_cols % 64 == 0 -> 64-column epilogue steps (tensor map box 64 x 32 / 32 x 64)
 };
 
 struct ProjParams {
@@ -63,6 +63,7 @@ struct ProjParams {
   int n_tiles_total;
   int nsplit;                    // column chunks per row unit (balance == 0)
   int balance;                   // 1: every cluster owns a contiguous range of the flat (row unit, column tile) sequence
+  long long* trace;              // debug (AF2_PROJ_TRACE=1): clock64 stamps of cluster 0's leader CTA, see tools/proj_trace.py
   int m_tiles;                   // ceil(T / 128)
 };
 
@@ -125,7 +126,9 @@ __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t*
 template <int EK, class Release>
 __device__ __forceinline__ void proj_epilogue_tile(uint8_t* wbuf, uint32_t& ec, uint32_t& gc, int grp, int lane, uint32_t t_acc,
                                                    const CUtensorMap* tmc, float rs, int m0w, int col0, int ncols,
-                                                   Release release) {
+                                                   Release release, long long* ctrace) {
+  // ctrace (debug, warp 4 of the traced CTA only): 5 stamps per chunk from slot 1024 + 5 * gc
+  auto cst = [&](int k) { if (ctrace && lane == 0 && gc < 200) ctrace[1024 + 5 * gc + k] = clock64(); };
   constexpr int mode = EpiTraits<EK>::mode, layout = EpiTraits<EK>::layout;
   constexpr bool gated = (mode == EPI_GATED_BF16);
   const int nchunks = (ncols + 31) / 32;
@@ -138,8 +141,10 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* wbuf, uint32_t& ec, 
   for (int cc = first; cc < nchunks; cc += 2) {
     uint32_t pk[16];
     tmem_ld_wait();
+    cst(0);
     if (cc + 2 >= nchunks) release();
     proj_finish32<EK>(u, g, rs, pk);
+    cst(1);
     if (cc + 2 < nchunks) {                         // next chunk's loads overlap staging + store of this one
       tmem_ld32(t_acc + (cc + 2) * 32, u);
       if constexpr (gated) tmem_ld32(t_acc + 128 + (cc + 2) * 32, g);
@@ -148,6 +153,7 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* wbuf, uint32_t& ec, 
     // the store that used this buffer two chunks ago must have read it (one newer store may still be in flight)
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
+    cst(2);
     if constexpr (layout == LAYOUT_TOKEN) {
       // [32 rows][64 B], 64B swizzle
 #pragma unroll
@@ -164,11 +170,81 @@ __device__ __forceinline__ void proj_epilogue_tile(uint8_t* wbuf, uint32_t& ec, 
     }
     fence_proxy_async_smem();
     __syncwarp();
+    cst(3);
     if (lane == 0) {
       if constexpr (layout == LAYOUT_TOKEN) tma_store_3d(tmc, eb, col0 + cc * 32, m0w, 0);
       else tma_store_3d(tmc, eb, m0w, col0 + cc * 32, 0);
       tma_store_commit();
     }
+    cst(4);
+    ++gc;
+  }
+}
+
+// Same tile, 64 output columns per step (segments whose width is a multiple of 64).  Tracing the 32-column version showed
+// ~650 cycles per chunk for ~50 instructions: the buffer-free wait, the proxy fence, the elected-thread TMA issue and the
+// loop turn-around each cost 100+ cycles regardless of the data they cover.  Here two 32-column halves are converted and
+// staged back to back into ONE 4 KB block (32 rows x 128 B, or 64 channels x 64 B) and leave with one fence and one store.
+template <int EK, class Release>
+__device__ __forceinline__ void proj_epilogue_tile_wide(uint8_t* wbuf, uint32_t& ec, uint32_t& gc, int grp, int lane, uint32_t t_acc,
+                                                        const CUtensorMap* tmc, float rs, int m0w, int col0, int ncols,
+                                                        Release release, long long* ctrace) {
+  constexpr int mode = EpiTraits<EK>::mode, layout = EpiTraits<EK>::layout;
+  constexpr bool gated = (mode == EPI_GATED_BF16);
+  auto cst = [&](int k) { if (ctrace && lane == 0 && gc < 200) ctrace[1024 + 5 * gc + k] = clock64(); };
+  const int nblk = ncols >> 6;
+  const int first = ((ec & 1) == static_cast<uint32_t>(grp)) ? 0 : 1;     // this warp's 64-column blocks: first, first + 2, ...
+  ec += nblk;
+  if (first >= nblk) { release(); return; }
+  uint32_t u[32], g[32];
+  tmem_ld32(t_acc + first * 64, u);
+  if constexpr (gated) tmem_ld32(t_acc + 128 + first * 64, g);
+  for (int b = first; b < nblk; b += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t pk[16];
+      tmem_ld_wait();
+      if (h == 0) cst(0);
+      if (h == 1 && b + 2 >= nblk) release();
+      proj_finish32<EK>(u, g, rs, pk);
+      if (h == 0) {                                   // the other half of this block
+        tmem_ld32(t_acc + b * 64 + 32, u);
+        if constexpr (gated) tmem_ld32(t_acc + 128 + b * 64 + 32, g);
+      } else if (b + 2 < nblk) {                      // first half of the warp's next block
+        tmem_ld32(t_acc + (b + 2) * 64, u);
+        if constexpr (gated) tmem_ld32(t_acc + 128 + (b + 2) * 64, g);
+      }
+      if (h == 0) {
+        cst(1);
+        if (lane == 0) tma_store_wait_read<0>();      // the previous store has drained the staging block
+        __syncwarp();
+        cst(2);
+      }
+      if constexpr (layout == LAYOUT_TOKEN) {
+        // [32 rows][128 B], 128B swizzle; this half fills 16-byte chunks 4h .. 4h+3 of the lane's row
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(wbuf + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      } else {
+        // [64 channels][32 tokens x 2 B], 64B swizzle; lane = token; this half fills channels 32h .. 32h+31
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t c0 = 32 * h + 2 * j, c1 = c0 + 1;
+          *reinterpret_cast<uint16_t*>(wbuf + c0 * 64 + ((((lane >> 3) ^ ((c0 >> 1) & 3)) << 4) | ((lane & 7) << 1))) = static_cast<uint16_t>(pk[j] & 0xffffu);
+          *reinterpret_cast<uint16_t*>(wbuf + c1 * 64 + ((((lane >> 3) ^ ((c1 >> 1) & 3)) << 4) | ((lane & 7) << 1))) = static_cast<uint16_t>(pk[j] >> 16);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    cst(3);
+    if (lane == 0) {
+      if constexpr (layout == LAYOUT_TOKEN) tma_store_3d(tmc, wbuf, col0 + b * 64, m0w, 0);
+      else tma_store_3d(tmc, wbuf, m0w, col0 + b * 64, 0);
+      tma_store_commit();
+    }
+    cst(4);
     ++gc;
   }
 }
@@ -398,6 +474,10 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     return s;
   };
 
+  const bool tr = p.trace != nullptr && cluster_id == 0 && rank == 0;
+  auto stamp = [&](int idx) { if (tr && lane == 0 && idx < 1023) p.trace[idx] = clock64(); };
+  if (tr && threadIdx.x == 0) p.trace[1023] = clock64();
+
   if (warp == 0) {
     // ================================ weight-tile TMA producer ================================
     if (lane == 0) {
@@ -444,10 +524,13 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
           const int acc = tcnt & 1;
           mbar_wait(&tempty_bar[acc], ((tcnt >> 1) & 1) ^ 1);
           tc_fence_after();
+          stamp(3 * static_cast<int>(tcnt));
           const uint32_t d_tmem = tmem_base + acc * 256;
           for (int kb = -1; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
+            if (kb < 0) stamp(3 * static_cast<int>(tcnt) + 1);
+            if (kb == nkb - 1) stamp(3 * static_cast<int>(tcnt) + 2);
             if (elect_one()) {
               const uint32_t sb = smem_u32(smem + L::B_OFF + stage * L::B_STAGE);
               if (kb < 0) {
@@ -509,8 +592,11 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const int col0 = (nt - sg.tile0) * W;
         const int ncols = min(W, sg.out_cols - col0);
         const CUtensorMap* tmc = sg.map == 0 ? &tmC0 : (sg.map == 1 ? &tmC1 : &tmC2);
+        const int tbase = (warp == 4) ? 256 : (warp == 8 ? 512 : 4096);
+        stamp(tbase + 3 * static_cast<int>(tcnt));
         mbar_wait(&tfull_bar[acc], (tcnt >> 1) & 1);
         tc_fence_after();
+        stamp(tbase + 3 * static_cast<int>(tcnt) + 1);
         const uint32_t t_acc = tmem_base + acc * 256 + lane_sel;
         // hand the accumulator stage back: this warp's TMEM loads of the tile have landed (8 * CTAS warps arrive)
         auto release = [&]() {
@@ -523,8 +609,14 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         };
 #define AF2_PROJ_CASE(EKV)                                                                                               \
   if constexpr ((KINDS & KBIT(EKV)) != 0) {                                                                              \
-    if (sg.kind == EKV)                                                                                                  \
-      proj_epilogue_tile<EKV>(wbuf, ec, gc, grp, lane, t_acc, tmc, rs, m0w, col0, ncols > 0 ? ncols : 0, release);       \
+    if (sg.kind == EKV) {                                                                                                \
+      if (sg.wide)                                                                                                       \
+        proj_epilogue_tile_wide<EKV>(wbuf, ec, gc, grp, lane, t_acc, tmc, rs, m0w, col0, ncols > 0 ? ncols : 0, release, \
+                                     (tr && warp == 4) ? p.trace : nullptr);                                             \
+      else                                                                                                               \
+        proj_epilogue_tile<EKV>(wbuf, ec, gc, grp, lane, t_acc, tmc, rs, m0w, col0, ncols > 0 ? ncols : 0, release,      \
+                                (tr && warp == 4) ? p.trace : nullptr);                                                  \
+    }                                                                                                                    \
   }
         AF2_PROJ_CASE(EK_STORE_TOK)
         AF2_PROJ_CASE(EK_STORE_TOK_SIG)
@@ -533,6 +625,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         AF2_PROJ_CASE(EK_GATED_TOK_GELU)
         AF2_PROJ_CASE(EK_GATED_CH_SIG)
 #undef AF2_PROJ_CASE
+        stamp(tbase + 3 * static_cast<int>(tcnt) + 2);
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -543,8 +636,12 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     afull_remote[0] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[0]), 0) : 0u;
     afull_remote[1] = (CTAS == 2) ? mapa_u32(smem_u32(&afull_bar[1]), 0) : 0u;
     auto item_row0 = [&](int it) { return static_cast<long long>(item_unit(it) * CTAS + static_cast<int>(rank)) * 128; };
-    auto wait_empty = [&](int it) { mbar_wait(&aempty_bar[it & 1], ((it >> 1) & 1) ^ 1); };
+    auto wait_empty = [&](int it) {
+      mbar_wait(&aempty_bar[it & 1], ((it >> 1) & 1) ^ 1);
+      if (warp == 12) stamp(768 + 2 * it);
+    };
     auto signal_full = [&](int it) {
+      if (warp == 12) stamp(768 + 2 * it + 1);
       if constexpr (CTAS == 2) mbar_arrive_cluster(afull_remote[it & 1]);
       else mbar_arrive(&afull_bar[it & 1]);
     };

@@ -35,6 +35,9 @@ int af2_check_device(void);
 /* 2 (default): LN->projection clusters run on the fused CTA-pair kernel; 1: its single-CTA variant; 0: unfused
  * LayerNorm + GEMM launches (also selectable with the environment variable AF2_PROJ_CTAS, read by af2_check_device) */
 void af2_set_proj_mode(int ctas);
+/* debug aid: with AF2_PROJ_TRACE=1 in the environment the fused projection kernel records clock64 stamps of one CTA
+ * (MMA issue, epilogue and producer progress per tile); this copies the 2048 stamps of the last launch to `out` */
+int af2_debug_proj_trace(long long* out);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 unsigned long long af2_launch_count(void);
