@@ -91,6 +91,10 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
   CUtensorMap tc[3], tb, tx;
   int tile0 = 0, kinds = 0;
   double flops = 0, bytes = (double)c.T * c.d * 4;
+  // one staging discipline per launch (the 64-column blocks and the 32-column chunks share the warps' 4 KB buffers with
+  // different reuse rules): wide only when every segment's width is a multiple of 64
+  bool all_wide = g_proj_wide != 0;
+  for (int i = 0; i < c.nseg; ++i) all_wide = all_wide && (c.seg[i].out_cols % 64) == 0;
   for (int i = 0; i < c.nseg; ++i) {
     const ProjOut& o = c.seg[i];
     p.seg[i].tile0 = tile0; p.seg[i].ntiles = o.ntiles; p.seg[i].kind = o.kind; p.seg[i].out_cols = o.out_cols; p.seg[i].map = i;
@@ -100,7 +104,7 @@ int launch_proj(const ProjCall& c, cudaStream_t s) {
     if (!aligned16(o.out) || (o.ld * 2) % 16) return fail(AF2_ERR_BAD_ARG, "proj: output %d not TMA-describable", i);
     // every epilogue warp stores from its private 4 KB staging block: 64 columns x 32 rows per store when the segment's
     // width allows it (128-byte rows, 128B swizzle; channel-major: 64 channels x 32 tokens, 64B swizzle), else 32 x 32
-    const bool wide = g_proj_wide && (o.out_cols % 64) == 0;
+    const bool wide = all_wide;
     p.seg[i].wide = wide ? 1 : 0;
     if (!chan) {
       unsigned long long dc[3] = {(unsigned long long)o.out_cols, (unsigned long long)c.T, 1ull};
