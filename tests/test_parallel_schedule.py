@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the axis-sharded Evoformer schedule (alphafold2_b200/parallel.py) reproduces the
+"""CPU, world_size 2 and 4, gloo: the axis-sharded Evoformer schedule (alphafold2_b200/parallel.py) reproduces the
 single-process oracle when its stage ops are the oracle math.  Checks slicing, all-to-all layouts, operand
 gathers and the collective order -- everything of the N>1 path except the CUDA kernels themselves."""
 import os
@@ -55,12 +55,12 @@ def _worker(rank, world, port, masked, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("masked", [False, True])
-def test_sharded_schedule_world2(masked):
+@pytest.mark.parametrize("masked,world", [(False, 2), (True, 2), (True, 4)])
+def test_sharded_schedule(masked, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, masked, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, masked, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
