@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node P tools/parallel_check.py : sharded trunk on P GPUs vs the single-GPU path and the oracle."""
+"""torchrun --nproc-per-node P tests/parallel_check_multi_gpu.py : sharded trunk on P GPUs vs the single-GPU path and the oracle."""
 import json
 import os
 import sys
@@ -6,7 +6,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import alphafold2_b200 as A  # noqa: E402

@@ -1,5 +1,5 @@
 """-m gpu: the sharded schedule with the CUDA stage ops.  With one rank (NCCL group of size 1) it must agree with the
-monolithic single-GPU modules and the fp64 oracle; tools/parallel_check.py repeats this on 2+ GPUs under torchrun."""
+monolithic single-GPU modules and the fp64 oracle; tests/parallel_check_multi_gpu.py repeats this on 2+ GPUs under torchrun."""
 import os
 
 import pytest
