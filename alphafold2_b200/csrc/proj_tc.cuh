@@ -20,9 +20,14 @@
 // The kernel is specialised at compile time on (pair / single CTA, set of epilogue kinds) so each instantiation carries
 // only the code it runs (the all-in-one version was instruction-cache bound).
 // Warp roles per CTA (512 threads): 0 weight-tile TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator |
-// 3 idle | 4..11 epilogue: each warp autonomous (its 32 TMEM lanes, every second 32-column chunk, two private 2 KB
-// staging buffers, its own TMA stores; no block barriers) | 12..15 LayerNorm producers (8 lanes per row).
+// 3 idle | 4..11 epilogue: each warp autonomous (its 32 TMEM lanes, every second 64-column block -- 32-column chunk when
+// a segment's width is not a multiple of 64 --, a private 4 KB staging area, its own TMA stores; no block barriers) |
+// 12..15 LayerNorm producers (8 lanes per row, packed fp32 math).
 // Accumulators are double buffered in TMEM (2 x 256 columns per CTA).
+// Work split: the flat sequence of (row unit of 256 rows, column tile) pairs is cut into one contiguous range per cluster.
+// A debug timeline of one CTA is available (ProjParams::trace, AF2_PROJ_TRACE=1, tools/proj_trace.py); DESIGN.md 10b
+// reads it: the steady state is bound by the epilogue's fixed per-step latencies, the q|k|v+gate launch additionally by
+// the rate at which HBM absorbs its 268 MB of output.
 #pragma once
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
