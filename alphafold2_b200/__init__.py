@@ -4,10 +4,11 @@
 """
 from .alphafold2 import (Alphafold2, Evoformer, EvoformerBlock, PairwiseAttentionBlock, MsaAttentionBlock,
                          AxialAttention, Attention, TriangleMultiplicativeModule, OuterMean, FeedForward,
-                         ReturnValues, Recyclables)
+                         ReturnValues, Recyclables, invalidate_packed)
+from .ops import set_precision
 from .rotary import apply_rotary_pos_emb, rotate_every_two, FixedPositionalEmbedding, AxialRotaryEmbedding
 
 __all__ = ["Alphafold2", "Evoformer", "EvoformerBlock", "PairwiseAttentionBlock", "MsaAttentionBlock",
            "AxialAttention", "Attention", "TriangleMultiplicativeModule", "OuterMean", "FeedForward",
            "ReturnValues", "Recyclables", "apply_rotary_pos_emb", "rotate_every_two",
-           "FixedPositionalEmbedding", "AxialRotaryEmbedding"]
+           "FixedPositionalEmbedding", "AxialRotaryEmbedding", "invalidate_packed", "set_precision"]

@@ -54,18 +54,81 @@ def exists(val):
 
 
 class _Packable(nn.Module):
-    """Caches the bf16-packed weights of a module, re-packing when any parameter was modified."""
+    """Caches the bf16-packed weights of a module, re-packing when a parameter was modified.
+
+    The cache key is (data_ptr, _version) of every parameter plus a global epoch: optimizer steps, ``copy_``,
+    ``load_state_dict``, ``.to()/.cuda()`` and ``train()/eval()`` are all seen.  Writes through ``param.data``
+    (``w.data.copy_()``, EMA ``p.data.mul_()``) change neither field in torch, so they need an explicit
+    ``alphafold2_b200.invalidate_packed(model)`` -- or run with ``AF2_PACK_CHECK=1``, which adds a content
+    fingerprint (one device sync per module and forward: a debugging aid, not the default)."""
 
     def _pack(self) -> ops.Packed:
         raise NotImplementedError
 
-    def packed(self) -> ops.Packed:
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters(recurse=True))
-        if getattr(self, "_pk_key", None) != key:
+    def _pack_key(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters(recurse=True)) + (ops.pack_epoch(), ops.precision_of(self))
+        if ops.PACK_CHECK:
             with torch.no_grad():
-                self._pk = self._pack()
-            self._pk_key = key
-        return self._pk
+                key += tuple(float(p.detach().double().sum()) + float(p.detach().double().abs().sum()) for p in self.parameters(recurse=True))
+        return key
+
+    def packed(self) -> ops.Packed:
+        key = self._pack_key()
+        if self.__dict__.get("_pk_key") != key:
+            with torch.no_grad():
+                self.__dict__["_pk"] = self._pack()
+            self.__dict__["_pk_key"] = key
+        return self.__dict__["_pk"]
+
+    def invalidate_packed(self):
+        self.__dict__.pop("_pk", None)
+        self.__dict__.pop("_pk_key", None)
+
+    # the packed cache holds ctypes structs (device pointers): never copied / pickled with the module
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_pk", None)
+        st.pop("_pk_key", None)
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_pk", "_pk_key"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+
+def invalidate_packed(module: nn.Module) -> None:
+    """Drop every cached packed-weight set under `module` (needed after in-place edits through ``param.data``)."""
+    ops.bump_pack_epoch()
+    for mod in module.modules():
+        if isinstance(mod, _Packable):
+            mod.invalidate_packed()
+
+
+def _forward_only(*tensors):
+    """SURVEY.md 8(b) error convention: the kernels are not differentiable.  Silently detaching would return wrong
+    (zero) gradients, so a call that autograd would have to record raises instead."""
+    if torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError("alphafold2_b200 is forward-only (hand-written sm_100a kernels, no autograd): call it under "
+                           "torch.no_grad() or pass tensors that do not require grad")
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -101,6 +164,7 @@ class FeedForward(_Packable):
         return ops.feed_forward_(self.packed(), x)
 
     def forward(self, x, **kwargs):
+        _forward_only(x)
         with torch.no_grad():
             res = _f32c(x)
             return (self.add_to_(res) - x).to(x.dtype)
@@ -160,6 +224,7 @@ class AxialAttention(_Packable):
         return ops.axial_attention_(self.packed(), x, self.attn.heads, self.attn.dim_head, bool(self.row_attn), edges, mask)
 
     def forward(self, x, edges=None, mask=None):
+        _forward_only(x, edges)
         with torch.no_grad():
             res = _f32c(x)
             e = None
@@ -205,6 +270,7 @@ class TriangleMultiplicativeModule(_Packable):
 
     def forward(self, x, mask=None):
         assert x.shape[1] == x.shape[2], 'feature map must be symmetrical'
+        _forward_only(x)
         with torch.no_grad():
             res = _f32c(x)
             return (self.add_to_(res, mask) - x).to(x.dtype)
@@ -234,6 +300,7 @@ class OuterMean(_Packable):
         return ops.outer_mean_(self.packed(), x, m, mask, self.eps)
 
     def forward(self, x, mask=None):
+        _forward_only(x)
         with torch.no_grad():
             m = x.detach().to(torch.float32).contiguous()
             b, _, n, d = m.shape
@@ -264,6 +331,7 @@ class PairwiseAttentionBlock(nn.Module):
         return x
 
     def forward(self, x, mask=None, msa_repr=None, msa_mask=None):
+        _forward_only(x, msa_repr)
         with torch.no_grad():
             mr = msa_repr.detach().to(torch.float32).contiguous() if exists(msa_repr) else None
             return self.update_(_f32c(x), mask, mr, msa_mask).to(x.dtype)
@@ -281,6 +349,7 @@ class MsaAttentionBlock(nn.Module):
         return m
 
     def forward(self, x, mask=None, pairwise_repr=None):
+        _forward_only(x, pairwise_repr)
         with torch.no_grad():
             pr = pairwise_repr.detach().to(torch.float32).contiguous() if exists(pairwise_repr) else None
             return self.update_(_f32c(x), mask, pr).to(x.dtype)
@@ -307,6 +376,7 @@ class EvoformerBlock(nn.Module):
 
     def forward(self, inputs):
         x, m, mask, msa_mask = inputs
+        _forward_only(x, m)
         with torch.no_grad():
             xo, mo = self.update_(_f32c(x), _f32c(m), mask, msa_mask)
         return xo.to(x.dtype), mo.to(m.dtype), mask, msa_mask
@@ -320,6 +390,7 @@ class Evoformer(nn.Module):
     def forward(self, x, m, mask=None, msa_mask=None):
         """x [b, N, N, d], m [b, S, N, d], mask [b, N, N] bool, msa_mask [b, S, N] bool -> (x, m).
         The reference's checkpoint_sequential(..., segments=1) is a plain sequential loop in forward."""
+        _forward_only(x, m)
         with torch.no_grad():
             xo, mo = _f32c(x), _f32c(m)
             mk = mask.bool().contiguous() if exists(mask) else None
@@ -404,6 +475,7 @@ class Alphafold2(nn.Module):
     ):
         assert not (self.disable_token_embed and not exists(seq_embed)), 'sequence embedding must be supplied if one has disabled token embedding'
         assert not (self.disable_token_embed and not exists(msa_embed)), 'msa embedding must be supplied if one has disabled token embedding'
+        _forward_only(seq_embed, msa_embed, embedds)
         for name, val in (("extra_msa", extra_msa), ("templates_feats", templates_feats),
                           ("templates_angles", templates_angles), ("recyclables", recyclables)):
             if exists(val):

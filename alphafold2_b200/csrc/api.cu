@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -42,16 +43,28 @@ int fail(int code, const char* fmt, ...) {
     if (_r != AF2_OK) return _r; \
   } while (0)
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Per-device state: the dynamic-shared-memory opt-in, the SM count and the cluster occupancy are properties of a
+// device, and one process may drive several (ops.py keeps per-device workspaces), so every cache is indexed by ordinal.
+constexpr int MAX_DEVICES = 64;
+int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
 }
+int sm_count() {
+  static int n[MAX_DEVICES] = {0};
+  const int dev = cur_dev();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+
+struct NvtxRange {   // one NVTX range per C-ABI call (sub-op granularity for nsys / ncu --nvtx)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // launch accounting + optional per-kernel-class CUDA-event profiling (bench.py roofline numbers)
@@ -157,11 +170,11 @@ template <int BN, int STAGES, bool MN, int EK>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                      const GemmParams& p, cudaStream_t s) {
   using L = GemmSmem<BN, STAGES>;
-  static bool configured = false;
+  static bool configured[MAX_DEVICES] = {false};
   auto kern = gemm_tc_kernel<BN, STAGES, MN, EK>;
-  if (!configured) {
+  if (!configured[cur_dev()]) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured[cur_dev()] = true;
   }
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const long long total = (long long)p.batch * m_tiles * p.num_ntiles;
@@ -342,11 +355,11 @@ int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_b
 template <int D>
 int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s) {
   using L = Chan2TokSmem<D>;
-  static bool configured = false;
+  static bool configured[MAX_DEVICES] = {false};
   auto kern = chan_to_token_tma_kernel<D>;
-  if (!configured) {
+  if (!configured[cur_dev()]) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured[cur_dev()] = true;
   }
   CUtensorMap tx, tg, ty;
   {
@@ -383,11 +396,11 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
   if (p.pitch == p.n && p.d % 64 == 0 && p.d <= 256 && (T % 4) == 0) {
     // dense token grid: 64-token tiles, fully coalesced
     const size_t smem = (size_t)p.d * 64 * sizeof(float) + 8 * 64 * 2 * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {false};
+    if (!configured[cur_dev()]) {
       CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 64 * 4 + 4096));
       CUDA_OK(cudaFuncSetAttribute(chan_to_token_tile_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 64 * 4 + 4096));
-      configured = true;
+      configured[cur_dev()] = true;
     }
     ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)T * p.d * (p.mode == 0 ? 8.0 : 6.0));
     const unsigned grid = (unsigned)((T + 63) / 64);
@@ -401,10 +414,10 @@ int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
     return AF2_OK;
   }
   const size_t smem = (size_t)p.d * 33 * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[MAX_DEVICES] = {0};
+  if (smem > 48 * 1024 && smem > configured[cur_dev()]) {
     CUDA_OK(cudaFuncSetAttribute(chan_to_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[cur_dev()] = smem;
   }
   dim3 grid((p.n + 31) / 32, p.rows);
   ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)p.rows * p.n * p.d * (p.mode == 0 ? 8.0 : 6.0));
@@ -420,11 +433,11 @@ template <int DH>
 int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tbias,
                           const CUtensorMap& tg, const CUtensorMap& to, const AttnParams& p, cudaStream_t s) {
   using L = AttnSmem<DH>;
-  static bool configured = false;
+  static bool configured[MAX_DEVICES] = {false};
   auto kern = attention_tc_kernel<DH>;
-  if (!configured) {
+  if (!configured[cur_dev()]) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured[cur_dev()] = true;
   }
   const long long items = (long long)((p.n + 127) / 128) * p.heads * p.nbatch;
   if (items <= 0) return AF2_OK;
@@ -479,10 +492,35 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
 
 #include "proj_launch.inl"
 
+// OuterMean normaliser of pair rows [row0, row0 + rows) of one batch element (quirk Q3): bit-packed kernel when the packed
+// mask fits in shared memory, else the byte-loop kernel
+int launch_outer_scale(const uint8_t* mask, float* scale, int row0, int rows, int S, int N, float eps, cudaStream_t s);
+
 int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)sm_count() * 8;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int launch_outer_scale(const uint8_t* mask, float* scale, int row0, int rows, int S, int N, float eps, cudaStream_t s) {
+  const long long T = (long long)rows * N;
+  if (T <= 0) return AF2_OK;
+  const size_t smem = (size_t)((S + 31) / 32) * N * 4;
+  ProfScope ps(s, KC_MISC, 0.0, 0.0);
+  if (smem <= 160 * 1024) {
+    static size_t configured[MAX_DEVICES] = {0};
+    if (smem > 48 * 1024 && smem > configured[cur_dev()]) {
+      CUDA_OK(cudaFuncSetAttribute(outer_scale_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[cur_dev()] = smem;
+    }
+    const long long need = (T + 255) / 256;
+    const int grid = (int)(need < sm_count() ? need : sm_count());
+    outer_scale_bits_kernel<<<grid, 256, smem, s>>>(mask, scale, row0, rows, S, N, eps);
+  } else {
+    outer_scale_rows_kernel<<<ew_grid(T), 256, 0, s>>>(mask, scale, row0, rows, S, N, eps);
+  }
+  CUDA_OK(cudaGetLastError());
+  return AF2_OK;
 }
 
 }  // namespace
@@ -559,6 +597,7 @@ long long af2_feed_forward_workspace(long long tokens, int d, int hidden) {
 
 int af2_feed_forward(const af2_ff_weights* w, float* x, long long tokens, int d, int hidden, void* workspace,
                      long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_feed_forward");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x) return fail(AF2_ERR_BAD_ARG, "feed_forward: null argument");
   if (d % 8 || hidden % 8) return fail(AF2_ERR_BAD_ARG, "feed_forward: d=%d and hidden=%d must be multiples of 8", d, hidden);
@@ -606,6 +645,7 @@ long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads
 static int axial_attention_impl(const af2_attn_weights* w, float* x, const float* edges, const void* pre_bias,
                                 const unsigned char* mask, int B, int h, int wdim, int d, int heads, int dim_head,
                                 int row_attn, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_(row_attn ? "af2_axial_attention(row)" : "af2_axial_attention(col)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x) return fail(AF2_ERR_BAD_ARG, "axial_attention: null argument");
   if (dim_head != 32 && dim_head != 64) return fail(AF2_ERR_BAD_ARG, "axial_attention: dim_head %d unsupported (32 or 64)", dim_head);
@@ -706,6 +746,7 @@ long long af2_triangle_multiply_workspace(int B, int N, int d) {
 
 int af2_triangle_multiply(const af2_trimul_weights* w, float* x, const unsigned char* mask, int B, int N, int d,
                           int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_triangle_multiply");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x) return fail(AF2_ERR_BAD_ARG, "triangle_multiply: null argument");
   if (d % 32) return fail(AF2_ERR_BAD_ARG, "triangle_multiply: dim %d must be a multiple of 32", d);
@@ -799,6 +840,7 @@ long long af2_outer_mean_workspace(int B, int S, int N, int d) {
 
 int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
                    int N, int d, float eps, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_outer_mean");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x || !m) return fail(AF2_ERR_BAD_ARG, "outer_mean: null argument");
   if (d % 32) return fail(AF2_ERR_BAD_ARG, "outer_mean: dim %d must be a multiple of 32", d);
@@ -823,8 +865,8 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   if (msa_mask) {
     if (!fused_front) { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm); }
     CUDA_OK(cudaGetLastError());
-    { ProfScope ps(s, KC_MISC, 0.0, 0.0); outer_scale_kernel<<<ew_grid(Tx), 256, 0, s>>>(msa_mask, scale, B, S, N, eps); }
-    CUDA_OK(cudaGetLastError());
+    for (int b = 0; b < B; ++b)
+      AF2_TRY(launch_outer_scale(msa_mask + (long long)b * S * N, scale + (long long)b * N * N, 0, N, S, N, eps, s));
   }
   if (np8 != N) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * cs_lr * 2, s));
   // [left | right] = (LN(m) W^T + b) * mask  -> channel-major [c][b*S + s][i]
@@ -880,6 +922,7 @@ int af2_axial_attention_prebias(const af2_attn_weights* w, float* x, const void*
 // bias rows of a shard of the pair tensor: out[h][r][j] (pitch npad, caller zero-fills the pad) = <x[r, j, :], w_edge[h, :]>
 int af2_pair_bias(const float* x_rows, const float* w_edge, void* bias_out, int rows, int n, int d, int heads,
                   af2_stream_t stream) {
+  NvtxRange nvtx_("af2_pair_bias");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!x_rows || !w_edge || !bias_out) return fail(AF2_ERR_BAD_ARG, "pair_bias: null argument");
   const int npad = (int)align_up(n, 8);
@@ -904,6 +947,7 @@ long long af2_triangle_project_workspace(long long tokens, int d) {
 int af2_triangle_project(const af2_trimul_weights* w, const float* x, const unsigned char* mask, long long tokens,
                          int inner, int d, void* Lc, void* Rc, long long chan_stride, void* gate, void* workspace,
                          long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_triangle_project");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x || !Lc || !Rc || !gate) return fail(AF2_ERR_BAD_ARG, "triangle_project: null argument");
   if (d % 32) return fail(AF2_ERR_BAD_ARG, "triangle_project: dim %d must be a multiple of 32", d);
@@ -961,6 +1005,7 @@ long long af2_triangle_contract_workspace(int rows, int cols, int d) {
 int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc, long long cs_l, const void* Rg,
                           long long cs_r, long long piece_stride, int pieces, const void* gate, int rows, int cols,
                           int K, int d, int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_triangle_contract");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x || !Lc || !Rg || !gate || pieces < 1) return fail(AF2_ERR_BAD_ARG, "triangle_contract: bad argument");
   if ((!ingoing && cols % pieces) || (ingoing && rows % pieces)) return fail(AF2_ERR_BAD_ARG, "triangle_contract: pieces must divide the gathered axis");
@@ -1014,6 +1059,7 @@ long long af2_outer_project_workspace(long long tokens, int d) {
 int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned char* msa_mask, long long tokens,
                       int inner, int d, void* LRc, long long chan_stride, void* workspace, long long workspace_bytes,
                       af2_stream_t stream) {
+  NvtxRange nvtx_("af2_outer_project");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !m || !LRc) return fail(AF2_ERR_BAD_ARG, "outer_project: null argument");
   if (d % 32) return fail(AF2_ERR_BAD_ARG, "outer_project: dim %d must be a multiple of 32", d);
@@ -1057,6 +1103,7 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
                        long long cs_r, long long piece_stride, int pieces, const unsigned char* msa_mask_full,
                        int row0, int rows, int N, int S, int d, float eps, void* workspace, long long workspace_bytes,
                        af2_stream_t stream) {
+  NvtxRange nvtx_("af2_outer_contract");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x || !Lc || !Rg || pieces < 1 || N % pieces) return fail(AF2_ERR_BAD_ARG, "outer_contract: bad argument");
   const long long T = (long long)rows * N;
@@ -1067,11 +1114,7 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
   __nv_bfloat16* tn = ar.take<__nv_bfloat16>(T * d);
   float* scale = ar.take<float>(T);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_contract: workspace too small");
-  if (msa_mask_full) {
-    ProfScope ps(s, KC_MISC, 0.0, 0.0);
-    outer_scale_rows_kernel<<<ew_grid(T), 256, 0, s>>>(msa_mask_full, scale, row0, rows, S, N, eps);
-    CUDA_OK(cudaGetLastError());
-  }
+  if (msa_mask_full) AF2_TRY(launch_outer_scale(msa_mask_full, scale, row0, rows, S, N, eps, s));
   const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
   const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
   const int pc = N / pieces;
@@ -1098,6 +1141,7 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
 // ------------------------------------------------------------------------------------------------
 int af2_rotary(const float* x, const float* sin_, const float* cos_, float* y, int b, int h, int n, int dh, int rot,
                int sincos_batch, af2_stream_t stream) {
+  NvtxRange nvtx_("af2_rotary");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dh % 2 || rot % 2 || rot > dh) return fail(AF2_ERR_BAD_ARG, "rotary: dh=%d rot=%d must be even, rot <= dh", dh, rot);
   const long long pairs = (long long)b * h * n * (dh / 2);

@@ -29,8 +29,10 @@ template <int CTAS, int KINDS>
 int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtensorMap& tx, ProjParams& p,
                      double flops, double bytes, cudaStream_t s) {
   using L = ProjSmem<CTAS>;
-  static bool configured = false;
-  static int max_clusters = 0;
+  static bool configured_dev[MAX_DEVICES] = {false};
+  static int max_clusters_dev[MAX_DEVICES] = {0};
+  bool& configured = configured_dev[cur_dev()];
+  int& max_clusters = max_clusters_dev[cur_dev()];
   auto kern = proj_tc_kernel<CTAS, KINDS>;
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));

@@ -14,6 +14,41 @@ from . import _lib
 _WORKSPACE: Dict[torch.device, torch.Tensor] = {}
 _DEVICE_CHECKED = set()
 
+# ---- packed-weight cache control (alphafold2._Packable) ----
+import os as _os
+
+PACK_CHECK = _os.environ.get("AF2_PACK_CHECK", "0") not in ("", "0")      # content fingerprint in the cache key (debug aid)
+_PACK_EPOCH = 0
+PRECISIONS = ("bf16", "strict")
+_DEFAULT_PRECISION = _os.environ.get("AF2_PRECISION", "bf16")
+if _DEFAULT_PRECISION not in PRECISIONS:
+    raise ValueError(f"AF2_PRECISION must be one of {PRECISIONS}, got {_DEFAULT_PRECISION!r}")
+
+
+def pack_epoch() -> int:
+    return _PACK_EPOCH
+
+
+def bump_pack_epoch() -> None:
+    global _PACK_EPOCH
+    _PACK_EPOCH += 1
+
+
+def precision_of(module) -> str:
+    """'bf16' (default: bf16 tensor-core operands, fp32 accumulate) or 'strict' (split-bf16 x3 operands, fp32-grade results
+    inside the north star's rtol 1e-3 / atol 1e-4 band).  Set per model with alphafold2_b200.set_precision()."""
+    return module.__dict__.get("_af2_precision", _DEFAULT_PRECISION)
+
+
+def set_precision(module, mode: str):
+    """Select the arithmetic of every hot-path module under `module`: 'bf16' or 'strict'.  Returns `module`."""
+    if mode not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {mode!r}")
+    for mod in module.modules():
+        mod.__dict__["_af2_precision"] = mode
+    return module
+
+
 
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -37,16 +72,41 @@ def _require(t: torch.Tensor, dtype, name: str):
         _DEVICE_CHECKED.add(dev)
 
 
+_WS_PRIVATE = None        # (dict device -> tensor, locked) while a CUDA graph owner captures (parallel._GraphedTrunk)
+
+
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer, reused by every op (ops on one stream are serialised)."""
+    """Grow-only per-device scratch buffer, reused by every op (ops on one stream are serialised).  Inside a
+    `private_workspace` scope the buffer belongs to the scope's owner (a captured CUDA graph keeps raw pointers into it)."""
     device = torch.device(device)
-    buf = _WORKSPACE.get(device)
+    store, locked = (_WORKSPACE, False) if _WS_PRIVATE is None else _WS_PRIVATE
+    buf = store.get(device)
     if buf is None or buf.numel() < nbytes:
+        if locked:
+            raise RuntimeError("workspace would have to grow during CUDA-graph capture (warm-up did not size it)")
         buf = None
-        _WORKSPACE.pop(device, None)
+        store.pop(device, None)
         buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
-        _WORKSPACE[device] = buf
+        store[device] = buf
     return buf
+
+
+class private_workspace:
+    """with private_workspace(store, locked): every op draws its scratch from `store` (dict owned by the caller)."""
+
+    def __init__(self, store: dict, locked: bool):
+        self.cfg = (store, locked)
+
+    def __enter__(self):
+        global _WS_PRIVATE
+        self.prev = _WS_PRIVATE
+        _WS_PRIVATE = self.cfg
+        return self
+
+    def __exit__(self, *exc):
+        global _WS_PRIVATE
+        _WS_PRIVATE = self.prev
+        return False
 
 
 def _mask_u8(mask: Optional[torch.Tensor], shape, name: str) -> Optional[torch.Tensor]:

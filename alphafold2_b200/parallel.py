@@ -19,6 +19,7 @@ schedule itself (slicing, layouts, collectives) under gloo with world_size 2.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional
 
 import torch
@@ -227,24 +228,58 @@ COLLECTIVES_PER_BLOCK = {"all_gather_small_bias": 3, "all_gather_operand": 3, "a
 
 GRAPH_ENABLED = True     # module switch: set False to force the eager schedule (bench.py does, around its per-launch profiling pass)
 
+_LIVE_GRAPHS = weakref.WeakSet()
+_TEARDOWN_HOOKED = False
+
 
 def graph_default() -> bool:
-    """CUDA-graph replay of the sharded forward is opt-in (AF2_SHARD_GRAPH=1 or shard_evoformer(use_graph=True)).
-    Measured at C2 on 2 B200s it brings the forward from 21-22 ms (eager, host bound) to 18.7 ms and reproduces the eager
-    result bit for bit, but a process that still owns such a graph when the NCCL communicator is torn down hangs in
-    teardown (seen with torch 2.11 / NCCL 2.28.9): call release_graphs(model) before dist.destroy_process_group()."""
+    """CUDA-graph replay of the sharded forward is the default (AF2_SHARD_GRAPH=0 or shard_evoformer(use_graph=False)
+    selects the eager schedule).  With the sequence split over P ranks the eager schedule is host bound; the replay is
+    bit-identical to it (tests/parallel_check_multi_gpu.py)."""
     import os
-    return os.environ.get("AF2_SHARD_GRAPH", "0") not in ("", "0")
+    return os.environ.get("AF2_SHARD_GRAPH", "1") not in ("", "0")
+
+
+def release_all_graphs() -> None:
+    """Drop every captured graph of this process.  A process that still owns a CUDA graph with NCCL nodes hangs when the
+    communicator is torn down (torch 2.11 / NCCL 2.28.9), so this runs automatically before
+    torch.distributed.destroy_process_group() and at interpreter exit (see _hook_teardown)."""
+    for g in list(_LIVE_GRAPHS):
+        g.release()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def _hook_teardown() -> None:
+    global _TEARDOWN_HOOKED
+    if _TEARDOWN_HOOKED:
+        return
+    _TEARDOWN_HOOKED = True
+    import atexit
+    import functools
+    atexit.register(release_all_graphs)
+    orig = dist.destroy_process_group
+
+    @functools.wraps(orig)
+    def destroy_process_group(*args, **kwargs):
+        release_all_graphs()
+        return orig(*args, **kwargs)
+
+    dist.destroy_process_group = destroy_process_group
+    try:
+        import torch.distributed.distributed_c10d as c10d
+        if getattr(c10d, "destroy_process_group", None) is orig:
+            c10d.destroy_process_group = destroy_process_group
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def release_graphs(model) -> None:
-    """Drop the captured graphs of a sharded model (must precede the destruction of the process group)."""
+    """Drop the captured graphs of a sharded model (kept for callers of round 1; teardown now does it on its own)."""
     evo = model.net if hasattr(model, "net") else model
     g = getattr(evo, "_af2_graph", None)
     if g is not None:
-        g.graph, g.outputs, g.inputs, g.key = None, None, None, None
-        import gc
-        gc.collect()
+        g.release()
         torch.cuda.synchronize()
 
 
@@ -253,10 +288,17 @@ class _GraphedTrunk:
 
     With the sequence split over P ranks the device work per block shrinks by P while the host still walks ~60 C calls
     and ~12 NCCL enqueues per block, so from P = 2 on the eager schedule is bound by the host.  The whole forward
-    (kernels, layout copies and NCCL collectives) is therefore captured once per (shapes, mask presence) and replayed;
-    every rank captures the same sequence of collectives.  Inputs are read from the tensors seen at capture time (kept
-    alive here); a call with other tensors copies into them first.  Outputs are returned as fresh tensors.  If capture is
-    not possible the eager schedule is used and the reason is printed once."""
+    (kernels, layout copies and NCCL collectives) is therefore captured once per signature and replayed; every rank
+    captures the same sequence of collectives.
+
+    What a captured graph bakes in, and how each is kept valid:
+      * input tensors: read from the tensors seen at capture time (kept alive here); other tensors are copied into them;
+      * packed weights: the Packed objects of every module are held here, and the signature contains the parameters'
+        (data_ptr, _version) sum + the pack epoch, so load_state_dict / optimizer steps / invalidate_packed() recapture;
+      * scratch: the capture runs inside a private workspace owned by this object (ops.private_workspace), so later eager
+        ops that grow the shared workspace cannot free memory the graph points into.
+    Outputs are returned as fresh tensors.  If capture is not possible the eager schedule is used and the reason is
+    printed once."""
 
     def __init__(self, evo, group):
         self.evo, self.group = evo, group
@@ -266,21 +308,38 @@ class _GraphedTrunk:
         self.outputs = None
         self.failed = None
         self.launches_per_replay = 0
+        self.ws = {}
+        self.packed = None
+        self._params = None
+        _LIVE_GRAPHS.add(self)
+
+    def release(self):
+        self.graph, self.outputs, self.inputs, self.key, self.packed = None, None, None, None, None
+        self.ws = {}
+        import gc
+        gc.collect()
 
     def _eager(self, x, m, mask, msa_mask):
         return sharded_evoformer_forward(self.evo, x, m, mask, msa_mask, self.group)
+
+    def _weights_key(self):
+        if self._params is None:
+            self._params = list(self.evo.parameters())
+        return (sum(p._version for p in self._params), sum(p.data_ptr() for p in self._params) & 0xffffffffffff,
+                _ops.pack_epoch(), _ops.precision_of(self.evo))
 
     def __call__(self, x, m, mask=None, msa_mask=None):
         if not GRAPH_ENABLED or self.failed is not None or not x.is_cuda:
             return self._eager(x, m, mask, msa_mask)
         key = (tuple(x.shape), tuple(m.shape), x.dtype, m.dtype, None if mask is None else tuple(mask.shape),
-               None if msa_mask is None else tuple(msa_mask.shape), x.device)
+               None if msa_mask is None else tuple(msa_mask.shape), x.device, self._weights_key())
         if key != self.key:
             try:
+                self.release()
                 self._capture(key, x, m, mask, msa_mask)
             except Exception as e:  # noqa: BLE001 - any capture failure falls back to the eager schedule
                 self.failed = repr(e)
-                self.graph = None
+                self.release()
                 import sys
                 print(f"[alphafold2_b200.parallel] CUDA-graph capture failed, running eagerly: {self.failed}", file=sys.stderr)
                 torch.cuda.synchronize()
@@ -292,18 +351,20 @@ class _GraphedTrunk:
         return self.outputs[0].clone(), self.outputs[1].clone()
 
     def _capture(self, key, x, m, mask, msa_mask):
+        from .alphafold2 import _Packable
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(2):                      # packs weights, sizes the workspace, initialises NCCL
+        self.ws = {}
+        with torch.cuda.stream(side), _ops.private_workspace(self.ws, False):
+            for _ in range(2):                      # packs weights, sizes the private workspace, initialises NCCL
                 self._eager(x, m, mask, msa_mask)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
+        self.packed = [mod.packed() for mod in self.evo.modules() if isinstance(mod, _Packable)]
         n0 = _lib.load().af2_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with _ops.private_workspace(self.ws, True), torch.cuda.graph(g):
             out = self._eager(x, m, mask, msa_mask)
         self.launches_per_replay = int(_lib.load().af2_launch_count() - n0)   # kernels of this library inside one replay
         self.graph, self.inputs, self.outputs, self.key = g, (x, m, mask, msa_mask), out, key
@@ -312,13 +373,15 @@ class _GraphedTrunk:
 def shard_evoformer(model, group=None, use_graph: Optional[bool] = None):
     """Make `model.net(x, m, mask=, msa_mask=)` (an Alphafold2 or an Evoformer) run the sharded schedule.  Every rank
     must call forward with identical (replicated) inputs and gets the full outputs back.  use_graph: replay the schedule
-    as one CUDA graph per input signature (see _GraphedTrunk and graph_default; default: AF2_SHARD_GRAPH, off)."""
+    as one CUDA graph per input signature (see _GraphedTrunk and graph_default; default on, AF2_SHARD_GRAPH=0 disables)."""
     evo = model.net if hasattr(model, "net") else model
     if getattr(evo, "_af2_sharded", False):
         return model
     if use_graph is None:
         use_graph = graph_default()
     graphed = _GraphedTrunk(evo, group) if use_graph else None
+    if graphed is not None:
+        _hook_teardown()
 
     def fwd(x, m, mask=None, msa_mask=None, _evo=evo):
         if graphed is not None:

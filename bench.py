@@ -113,11 +113,32 @@ def randomize_zero_init_(model, std=0.02, seed=1234):
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference (the Python reference itself cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_block_sample(literal_ok=False):
-    """Times ONE Evoformer block of the C2 workload on the host cores (fp32); the forward is 12 identical blocks.
-    Default: the oracle's einsum OuterMean (validated against the reference), which is several times FASTER on a CPU
-    than the reference's literal (S,N,N,d) materialisation (alphafold2.py:341, 73 % of its block time)
-    -- i.e. the CPU baseline reported here is conservative (stronger than the reference itself)."""
+def host_threads():
+    """All the host threads the CPU arm can use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the count is set
+    explicitly (SURVEY.md 8d / BASELINE.md 3.3: torch.set_num_threads(os.cpu_count()))."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def make_config(world):
+    """One config dict for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD,
+            "parallelism": "single GPU" if world == 1 else
+            f"1 sequence axis-sharded over {world} GPUs (MSA-row / pair-row shards; per block 6 all-gathers + 6 all-to-alls over NCCL)",
+            "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
+            "accumulate": "fp32", "residual_stream": "fp32"}
+
+
+def cpu_block_sample(literal=False):
+    """One Evoformer block of the C2 workload on the host cores (fp32); the forward is 12 identical blocks.
+    literal=False: the oracle's einsum OuterMean (validated against the reference), several times FASTER on a CPU than the
+    reference's literal (S,N,N,d) materialisation (alphafold2.py:341, 73 % of its block time) -- a conservative
+    baseline.  literal=True follows alphafold2.py:341-349 line by line (needs ~18 GB of RSS at C2)."""
     from oracle import evoformer_oracle as O
     import alphafold2_b200 as A
     torch.manual_seed(0)
@@ -129,54 +150,114 @@ def cpu_block_sample(literal_ok=False):
     m = torch.randn(1, N_SEQ, N_RES, d)
     mask = torch.ones(1, N_RES, N_RES, dtype=torch.bool)
     msa_mask = torch.ones(1, N_SEQ, N_RES, dtype=torch.bool)
-    literal = literal_ok
-    try:
-        import psutil
-        literal = literal and psutil.virtual_memory().available > 40 * 2 ** 30   # alphafold2.py:341 needs ~18 GB RSS here
-    except Exception:
-        literal = False
 
     def step():
         t0 = time.perf_counter()
         with torch.no_grad():
             O.evoformer_block(w, "", x, m, H, mask, msa_mask, literal_outer=literal)
         return time.perf_counter() - t0
-    return step, literal
+    return step
+
+
+def literal_ok():
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 40 * 2 ** 30
+    except Exception:
+        return False
 
 
 def cpu_baseline(max_seconds=30.0):
-    step, literal = cpu_block_sample()
+    """Bounded sample on the host cores (rank 0, N = 1 only): one block with the einsum OuterMean (the reported value) and,
+    when the box has the memory, one block with the reference's literal OuterMean next to it."""
+    cores = host_threads()
+    step = cpu_block_sample(False)
     t = step()
     if t < max_seconds / 3:
         t = min(t, step())
     fwd = t * CFG["depth"]
-    return {"value": N_RES * N_RES / fwd, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 of {CFG['depth']} Evoformer blocks of the C2 workload (fp32 torch CPU oracle port, "
-                      f"{'literal (S,N,N,d) OuterMean as alphafold2.py:341' if literal else 'einsum OuterMean'}), "
-                      f"{t:.2f} s/block x {CFG['depth']}",
-            "seconds_per_block": t}
+    out = {"value": N_RES * N_RES / fwd, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"1 of {CFG['depth']} Evoformer blocks of the C2 workload (fp32 torch CPU oracle port, einsum OuterMean), "
+                     f"{t:.2f} s/block x {CFG['depth']}",
+           "seconds_per_block": t}
+    if literal_ok():
+        try:
+            tl = cpu_block_sample(True)()
+            out["literal_outer_seconds_per_block"] = tl
+            out["literal_outer_value"] = N_RES * N_RES / (tl * CFG["depth"])
+            out["sample"] += f"; same block with the literal (S,N,N,d) OuterMean of alphafold2.py:341: {tl:.2f} s/block"
+        except Exception as ex:  # noqa: BLE001
+            out["literal_outer_error"] = repr(ex)[:200]
+    return out
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU path (oracle port; the Python reference cannot travel to the GPU box) on all host
+    threads.  A step is a bounded sample of the C2 forward: ONE of its 12 identical Evoformer blocks; `ms_per_step` is the
+    measured time of that sample, `value` the residue-pairs/s of the whole forward it implies (N^2 / (12 x block))."""
     if rank != 0:
         return
-    step, literal = cpu_block_sample()
-    for _ in range(min(args.warmup, 1)):
+    cores = host_threads()
+    step = cpu_block_sample(False)
+    budget = float(os.environ.get("AF2_REF_BUDGET_S", "420"))
+    t_start = time.perf_counter()
+    warm = 0
+    for _ in range(args.warmup):
         step()
-    times = [step() for _ in range(args.steps)]
+        warm += 1
+        if time.perf_counter() - t_start > budget * 0.3:
+            break
+    times = []
+    for _ in range(args.steps):
+        times.append(step())
+        if time.perf_counter() - t_start > budget:
+            break
     t_blk = sum(times) / len(times)
     fwd = t_blk * CFG["depth"]
     val = N_RES * N_RES / fwd
-    sample = f"each step = 1 of {CFG['depth']} Evoformer blocks of the C2 workload on the host cores (fp32 oracle port, " \
-             f"{'literal OuterMean' if literal else 'einsum OuterMean'}); forward = {CFG['depth']} x block"
+    sample = f"each step = 1 of {CFG['depth']} Evoformer blocks of the C2 workload on {cores} host threads (fp32 oracle port, " \
+             f"einsum OuterMean); forward = {CFG['depth']} x block; value = N_res^2 / forward"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": fwd * 1e3, "ms_per_block": t_blk * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path (oracle/evoformer_oracle.py)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm, "ms_per_step": t_blk * 1e3, "ms_per_block": t_blk * 1e3, "ms_per_forward": fwd * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": make_config(world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def gpu_torch_baseline(dev, x0, m0, x_mask, msa_mask, model):
+    """Same-silicon yardstick, OUTSIDE every timed region of this repo's arm: the oracle port of the
+    reference trunk run by stock PyTorch (ATen / cuBLAS) on this GPU in fp32 and under autocast-bf16."""
+    from oracle import evoformer_oracle as O
+    w = {k[len("net."):]: v.detach() for k, v in model.state_dict().items() if k.startswith("net.")}
+    out = {}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for name, ctx in (("fp32", None), ("autocast_bf16", torch.autocast("cuda", dtype=torch.bfloat16))):
+            def fwd():
+                with torch.no_grad():
+                    if ctx is None:
+                        return O.evoformer(w, "", x0, m0, CFG["heads"], CFG["depth"], x_mask, msa_mask, chunk=64)
+                    with ctx:
+                        return O.evoformer(w, "", x0, m0, CFG["heads"], CFG["depth"], x_mask, msa_mask, chunk=64)
+            fwd()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                fwd()
+            b.record()
+            b.synchronize()
+            ms = a.elapsed_time(b) / 3
+            out[name] = {"ms_per_step": ms, "value": N_RES * N_RES / (ms * 1e-3), "unit": UNIT}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out["what"] = "oracle port of the reference trunk (einsum OuterMean) executed by stock PyTorch eager on the same B200; not part of any timed region"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -327,11 +408,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_step, "ms_per_block": ms_step / CFG["depth"], "higher_is_better": True,
         "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": "single GPU" if world == 1 else
-                   f"1 sequence axis-sharded over {world} GPUs (MSA-row / pair-row shards; per block 6 all-gathers + 6 all-to-alls over NCCL"
-                   + ("; the whole forward replayed as one CUDA graph per rank)" if (graphed is not None and graphed.graph is not None) else ")"),
-                   "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
-                   "accumulate": "fp32", "residual_stream": "fp32"},
+        "config": make_config(world),
+        "schedule": ("eager" if world == 1 else ("CUDA graph replay per rank" if (graphed is not None and graphed.graph is not None) else "eager")),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -351,6 +429,10 @@ def run_ours(args, rank, world, local_rank):
             except Exception as ex:  # noqa
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                        "sample": f"failed: {ex}"}
+            try:
+                out["gpu_torch_baseline"] = gpu_torch_baseline(dev, x0, m0, x_mask, msa_mask, model)
+            except Exception as ex:  # noqa
+                out["gpu_torch_baseline"] = {"error": repr(ex)[:300]}
         print(json.dumps(out), flush=True)
     if world > 1:
         from alphafold2_b200.parallel import release_graphs

@@ -121,7 +121,7 @@ def axial_attention(w: W, p: str, x: Tensor, heads: int, row_attn: bool,
             bb = None
             if bias is not None:
                 # folded index = b_idx * axial + r  ->  bias of batch b_idx
-                idx = torch.arange(s, e) // axial
+                idx = torch.arange(s, e, device=bias.device) // axial
                 bb = bias[idx]
             outs.append(attention(w, p + "attn.", xf[s:e], heads, None if mf is None else mf[s:e], bb))
         of = torch.cat(outs, dim=0)
@@ -256,7 +256,7 @@ def alphafold2_distogram(w: W, seq: Tensor, msa: Optional[Tensor], mask: Optiona
     xl, xr = pr.chunk(2, dim=-1)
     x = xl[:, :, None, :] + xr[:, None, :, :]
     x_mask = (mask[:, :, None] & mask[:, None, :]) if mask is not None else None
-    idx = torch.arange(n)
+    idx = torch.arange(n, device=seq.device)
     rel = (idx[:, None] - idx[None, :]).clamp(-max_rel_dist, max_rel_dist) + max_rel_dist
     x = x + w["pos_emb.weight"].to(dtype)[rel][None]
     x, m = evoformer(w, "net.", x, m, heads, depth, x_mask, msa_mask, literal_outer, chunk)
