@@ -34,6 +34,23 @@ class OuterWeights(C.Structure):
                 ("w_cat", vp), ("b_cat", vp), ("w_ext", vp), ("w_ext_out", vp)]
 
 
+class FFWeightsStrict(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp)]
+
+
+class AttnWeightsStrict(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_qkvg", vp), ("b_qkvg", vp), ("w_out", vp), ("b_out", vp), ("w_edge", vp)]
+
+
+class TriMulWeightsStrict(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w5", vp), ("b5", vp), ("on_gamma", vp), ("on_beta", vp),
+                ("w_out", vp), ("b_out", vp)]
+
+
+class OuterWeightsStrict(C.Structure):
+    _fields_ = [("ln_gamma", vp), ("ln_beta", vp), ("w_lr", vp), ("b_lr", vp), ("w_out", vp), ("b_out", vp)]
+
+
 _SIGNATURES = {
     "af2_last_error": (C.c_char_p, []),
     "af2_abi_version": (ci, []),
@@ -46,6 +63,7 @@ _SIGNATURES = {
     "af2_feed_forward": (ci, [C.POINTER(FFWeights), vp, ll, ci, ci, vp, ll, vp]),
     "af2_feed_forward_workspace": (ll, [ll, ci, ci]),
     "af2_axial_attention": (ci, [C.POINTER(AttnWeights), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_axial_attention_ex": (ci, [C.POINTER(AttnWeights), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),
     "af2_axial_attention_workspace": (ll, [ci, ci, ci, ci, ci, ci, ci]),
     "af2_triangle_multiply": (ci, [C.POINTER(TriMulWeights), vp, vp, ci, ci, ci, ci, vp, ll, vp]),
     "af2_triangle_multiply_workspace": (ll, [ci, ci, ci]),
@@ -64,6 +82,20 @@ _SIGNATURES = {
     "af2_rotary": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "af2_layernorm_bf16": (ci, [vp, vp, vp, vp, ll, ci, cf, vp]),
     "af2_gemm_bf16_f32": (ci, [vp, ll, ll, vp, ll, ll, vp, ll, ll, ci, ci, ci, ci, ci, vp]),
+    # strict precision mode (split-bf16 x3 operands)
+    "af2_feed_forward_strict": (ci, [C.POINTER(FFWeightsStrict), vp, ll, ci, ci, vp, ll, vp]),
+    "af2_feed_forward_strict_workspace": (ll, [ll, ci, ci]),
+    "af2_axial_attention_strict": (ci, [C.POINTER(AttnWeightsStrict), vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_axial_attention_strict_workspace": (ll, [ci, ci, ci, ci, ci, ci, ci]),
+    "af2_triangle_multiply_strict": (ci, [C.POINTER(TriMulWeightsStrict), vp, vp, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_triangle_multiply_strict_workspace": (ll, [ci, ci, ci]),
+    "af2_outer_mean_strict": (ci, [C.POINTER(OuterWeightsStrict), vp, vp, vp, ci, ci, ci, ci, cf, vp, ll, vp]),
+    "af2_outer_mean_strict_workspace": (ll, [ci, ci, ci, ci]),
+    "af2_embed_pair_init_workspace": (ll, [ci, ci, ci]),
+    "af2_embed_pair_init": (ci, [vp, vp, vp, ci, vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ll, vp]),
+    "af2_distogram_head": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "af2_split_bf16": (ci, [vp, vp, ll, ci, vp]),
+    "af2_gemm_split_f32": (ci, [vp, vp, vp, ll, ci, ci, ci, ci, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -156,7 +156,8 @@ class FeedForward(_Packable):
         nn.init.zeros_(self.net[-1].bias)
 
     def _pack(self):
-        return ops.pack_feed_forward(self.norm.weight, self.norm.bias, self.net[0].weight, self.net[0].bias,
+        fn = ops.pack_feed_forward_strict if ops.precision_of(self) == "strict" else ops.pack_feed_forward
+        return fn(self.norm.weight, self.norm.bias, self.net[0].weight, self.net[0].bias,
                                      self.net[3].weight, self.net[3].bias)
 
     def add_to_(self, x):
@@ -214,14 +215,14 @@ class AxialAttention(_Packable):
     def _pack(self):
         a = self.attn
         we = self.edges_to_attn_bias[0].weight if self.edges_to_attn_bias is not None else None
-        return ops.pack_attention(self.norm.weight, self.norm.bias, a.to_q.weight, a.to_kv.weight, a.gating.weight,
+        fn = ops.pack_attention_strict if ops.precision_of(self) == "strict" else ops.pack_attention
+        return fn(self.norm.weight, self.norm.bias, a.to_q.weight, a.to_kv.weight, a.gating.weight,
                                   a.gating.bias, a.to_out.weight, a.to_out.bias, we, a.dim_head)
 
     def add_to_(self, x, edges=None, mask=None):
         assert self.row_attn ^ self.col_attn, 'has to be either row or column attention, but not both'
-        if self.global_query_attn:
-            raise NotImplementedError("global (tied-row) column attention of the extra-MSA stack is outside the hot path")
-        return ops.axial_attention_(self.packed(), x, self.attn.heads, self.attn.dim_head, bool(self.row_attn), edges, mask)
+        return ops.axial_attention_(self.packed(), x, self.attn.heads, self.attn.dim_head, bool(self.row_attn), edges, mask,
+                                    tied=bool(self.global_query_attn))
 
     def forward(self, x, edges=None, mask=None):
         _forward_only(x, edges)
@@ -259,7 +260,8 @@ class TriangleMultiplicativeModule(_Packable):
         self.to_out = nn.Linear(hidden_dim, dim)
 
     def _pack(self):
-        return ops.pack_triangle_multiply(
+        fn = ops.pack_triangle_multiply_strict if ops.precision_of(self) == "strict" else ops.pack_triangle_multiply
+        return fn(
             self.norm.weight, self.norm.bias, self.left_proj.weight, self.left_proj.bias, self.right_proj.weight,
             self.right_proj.bias, self.left_gate.weight, self.left_gate.bias, self.right_gate.weight,
             self.right_gate.bias, self.out_gate.weight, self.out_gate.bias, self.to_out_norm.weight,
@@ -292,7 +294,8 @@ class OuterMean(_Packable):
         self.proj_out = nn.Linear(hidden_dim, dim)
 
     def _pack(self):
-        return ops.pack_outer_mean(self.norm.weight, self.norm.bias, self.left_proj.weight, self.left_proj.bias,
+        fn = ops.pack_outer_mean_strict if ops.precision_of(self) == "strict" else ops.pack_outer_mean
+        return fn(self.norm.weight, self.norm.bias, self.left_proj.weight, self.left_proj.bias,
                                    self.right_proj.weight, self.right_proj.bias, self.proj_out.weight, self.proj_out.bias)
 
     def add_to_(self, x, m, mask=None):
@@ -399,6 +402,18 @@ class Evoformer(nn.Module):
                 layer.update_(xo, mo, mk, mmk)
         return xo.to(x.dtype), mo.to(m.dtype)
 
+    def run_(self, x, m, mask=None, msa_mask=None):
+        """Same as forward, for callers that own fp32 contiguous x / m and allow them to be updated in place (no private
+        copies).  A sharded trunk (parallel.shard_evoformer replaces `forward`) goes through its schedule instead."""
+        if "forward" in self.__dict__ or x.dtype != torch.float32 or m.dtype != torch.float32 or not (x.is_contiguous() and m.is_contiguous()):
+            return self(x, m, mask=mask, msa_mask=msa_mask)
+        with torch.no_grad():
+            mk = mask.bool().contiguous() if exists(mask) else None
+            mmk = msa_mask.bool().contiguous() if exists(msa_mask) else None
+            for layer in self.layers:
+                layer.update_(x, m, mk, mmk)
+        return x, m
+
 
 # ------------------------------------------------------------------------------------------------------
 # Alphafold2 shell (alphafold2.py:469-905): constructor + distogram forward; trunk call at :802-807
@@ -476,10 +491,9 @@ class Alphafold2(nn.Module):
         assert not (self.disable_token_embed and not exists(seq_embed)), 'sequence embedding must be supplied if one has disabled token embedding'
         assert not (self.disable_token_embed and not exists(msa_embed)), 'msa embedding must be supplied if one has disabled token embedding'
         _forward_only(seq_embed, msa_embed, embedds)
-        for name, val in (("extra_msa", extra_msa), ("templates_feats", templates_feats),
-                          ("templates_angles", templates_angles), ("recyclables", recyclables)):
+        for name, val in (("templates_feats", templates_feats), ("templates_angles", templates_angles), ("recyclables", recyclables)):
             if exists(val):
-                raise NotImplementedError(f"{name}: templates / extra-MSA stack / recycling are outside the B200 hot path (SURVEY.md §8f)")
+                raise NotImplementedError(f"{name}: templates / recycling are outside the B200 hot path (SURVEY.md §8f n3 / n4)")
         if self.training and not self._warned_training:
             warnings.warn("alphafold2_b200 is forward-only: running inference semantics (no MLM noising, no autograd)")
             self._warned_training = True
@@ -492,38 +506,65 @@ class Alphafold2(nn.Module):
             b, n = seq.shape[:2]
             device = seq.device
 
-            x = self.token_emb(seq) if not self.disable_token_embed else 0
-            if exists(seq_embed):
-                x = x + seq_embed
-            if exists(msa):
-                m = self.token_emb(msa) if not self.disable_token_embed else 0
-                if exists(msa_embed):
-                    m = m + msa_embed
-                m = m + x[:, None]
+            fused_glue = seq.is_cuda and not self.disable_token_embed and exists(msa)
+            if fused_glue:
+                # alphafold2.py:676-726 as fused kernels: embedding gather, m = emb[msa] + emb[seq], pair init
                 if not exists(msa_mask):
                     msa_mask = torch.ones_like(msa).bool()
-            elif exists(embedds):
-                m = self.embedd_project(embedds)
-                if not exists(msa_mask):
-                    msa_mask = torch.ones_like(embedds[..., -1]).bool()
+                x, m = ops.embed_pair_init(seq, msa, self.token_emb.weight, self.to_pairwise_repr.weight, self.to_pairwise_repr.bias,
+                                           self.pos_emb.weight, self.max_rel_dist, seq_embed, msa_embed, seq_index)
+            else:
+                x = self.token_emb(seq) if not self.disable_token_embed else 0
+                if exists(seq_embed):
+                    x = x + seq_embed
+                if exists(msa):
+                    m = self.token_emb(msa) if not self.disable_token_embed else 0
+                    if exists(msa_embed):
+                        m = m + msa_embed
+                    m = m + x[:, None]
+                    if not exists(msa_mask):
+                        msa_mask = torch.ones_like(msa).bool()
+                elif exists(embedds):
+                    m = self.embedd_project(embedds)
+                    if not exists(msa_mask):
+                        msa_mask = torch.ones_like(embedds[..., -1]).bool()
 
-            x_left, x_right = self.to_pairwise_repr(x).chunk(2, dim=-1)
-            x = x_left[:, :, None, :] + x_right[:, None, :, :]
+                x_left, x_right = self.to_pairwise_repr(x).chunk(2, dim=-1)
+                x = x_left[:, :, None, :] + x_right[:, None, :, :]
+                seq_index = seq_index if exists(seq_index) else torch.arange(n, device=device)
+                rel = (seq_index[None, :, None] - seq_index[None, None, :]).clamp(-self.max_rel_dist, self.max_rel_dist) + self.max_rel_dist
+                x = x + self.pos_emb(rel)
+                x, m = x.float().contiguous(), m.float().contiguous()
             x_mask = (mask[:, :, None] & mask[:, None, :]) if exists(mask) else None
 
-            seq_index = seq_index if exists(seq_index) else torch.arange(n, device=device)
-            rel = (seq_index[None, :, None] - seq_index[None, None, :]).clamp(-self.max_rel_dist, self.max_rel_dist) + self.max_rel_dist
-            x = x + self.pos_emb(rel)
+            if exists(extra_msa):
+                # alphafold2.py:789-798, reproduced WITH its quirks (do not "fix"): the stack embeds `msa`, not
+                # `extra_msa` (:790); only its pair output is kept; the default mask torch.ones_like(extra_m) has the
+                # embedding's rank and makes the reference fail in its first mask fold -- same here (ValueError).
+                extra_m = self.token_emb(msa).float().contiguous()
+                em = extra_msa_mask if exists(extra_msa_mask) else torch.ones_like(extra_m).bool()
+                if em.dim() != 3:
+                    raise ValueError("extra_msa_mask must be given with shape [b, n_msa, n] (the reference's default, "
+                                     "alphafold2.py:791, has the wrong rank and fails in einops too)")
+                x, _ = self.extra_msa_evoformer.run_(x.contiguous(), extra_m, mask=x_mask, msa_mask=em)
 
-            x, m = self.net(x, m, mask=x_mask, msa_mask=msa_mask)     # alphafold2.py:802-807
+            x, m = self.net.run_(x, m, mask=x_mask, msa_mask=msa_mask)     # alphafold2.py:802-807
 
             ret = ReturnValues()
             if self.predict_angles:
                 ret.theta_logits = self.to_prob_theta(x)
                 ret.phi_logits = self.to_prob_phi(x)
-            trunk_embeds = (x + x.transpose(1, 2)) * 0.5
-            ret.distance = self.to_distogram_logits(trunk_embeds)
+            ln, lin = self.to_distogram_logits[0], self.to_distogram_logits[1]
+            if x.is_cuda and x.dtype == torch.float32 and ops.distogram_head_ok(x.shape[-1], lin.weight.shape[0]):
+                # alphafold2.py:821-823 in one kernel: symmetrise + LayerNorm + Linear(d -> 37)
+                ret.distance = ops.distogram_head(x.contiguous(), ln.weight, ln.bias, lin.weight, lin.bias)
+                trunk_embeds = None
+            else:
+                trunk_embeds = (x + x.transpose(1, 2)) * 0.5
+                ret.distance = self.to_distogram_logits(trunk_embeds)
             if self.predict_angles:
+                if self.symmetrize_omega and trunk_embeds is None:
+                    trunk_embeds = (x + x.transpose(1, 2)) * 0.5
                 ret.omega_logits = self.to_prob_omega(trunk_embeds if self.symmetrize_omega else x)
             if not self.predict_coords or return_trunk:
                 return ret

@@ -17,6 +17,8 @@
 #include "gemm_tc.cuh"
 #include "proj_tc.cuh"
 #include "simt_kernels.cuh"
+#include "strict_kernels.cuh"
+#include "glue_kernels.cuh"
 
 using namespace af2;
 
@@ -164,6 +166,8 @@ struct GemmCall {
   const float* bias; const float* rowscale; const float* resid; long long ld_resid;
   int cm_inner, cm_pitch;
   int out_cols;           // 0: N (N/2 for GATED); else explicit number of valid output columns
+  // split-bf16 operands (strict precision, GemmParams::nseg): nseg = 3, a_half / b_half = element stride between the hi and lo planes
+  int nseg; long long a_half, b_half;
 };
 
 template <int BN, int STAGES, bool MN, int EK>
@@ -180,7 +184,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   const long long total = (long long)p.batch * m_tiles * p.num_ntiles;
   if (total <= 0) return AF2_OK;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  const double flops = 2.0 * p.batch * (double)p.M * p.N * p.K;
+  const double flops = 2.0 * p.batch * (double)p.M * p.N * p.K;    // algorithmic (a split-operand launch issues 3x this)
   const double obytes = (p.tile.mode == EPI_STORE_BF16 ? 2.0 : (p.tile.mode == EPI_GATED_BF16 ? 1.0 : (p.tile.mode == EPI_RESID_F32 ? 8.0 : 4.0)));
   const double bytes = p.batch * ((double)p.M * p.K * 2 + (p.batch > 1 ? (double)p.N * p.K * 2 : 0) + (double)p.M * p.N * obytes) +
                        (p.batch > 1 ? 0 : (double)p.N * p.K * 2);
@@ -194,7 +198,28 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
   if (c.M <= 0 || c.N <= 0 || c.K <= 0 || c.batch <= 0) return AF2_OK;
   CUtensorMap ta, tb;
   const int BN = c.bn;
-  if (!c.mn_major) {
+  if (c.nseg > 1) {
+    // rank-4 maps (k | mn, row | k, plane, batch) over split-bf16 operands
+    const unsigned long long ab = (unsigned long long)(c.batch > 1 ? c.a_batch : 0) * 2, bb_ = (unsigned long long)(c.batch > 1 ? c.b_batch : 0) * 2;
+    if (!c.mn_major) {
+      unsigned long long da[4] = {(unsigned long long)c.K, (unsigned long long)c.M, 2ull, (unsigned long long)c.batch};
+      unsigned long long sa[3] = {(unsigned long long)c.lda * 2, (unsigned long long)c.a_half * 2, ab ? ab : (unsigned long long)c.a_half * 4};
+      unsigned ba[4] = {64, 128, 1, 1};
+      AF2_TRY(make_tmap(&ta, c.A, 4, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B));
+      unsigned long long db[4] = {(unsigned long long)c.K, (unsigned long long)c.N, 2ull, (unsigned long long)c.batch};
+      unsigned long long sb[3] = {(unsigned long long)c.ldb * 2, (unsigned long long)c.b_half * 2, bb_ ? bb_ : (unsigned long long)c.b_half * 4};
+      unsigned bx[4] = {64, (unsigned)BN, 1, 1};
+      AF2_TRY(make_tmap(&tb, c.Bm, 4, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+    } else {
+      unsigned long long da[4] = {(unsigned long long)c.M, (unsigned long long)c.K, 2ull, (unsigned long long)c.batch};
+      unsigned long long sa[3] = {(unsigned long long)c.lda * 2, (unsigned long long)c.a_half * 2, ab ? ab : (unsigned long long)c.a_half * 4};
+      unsigned bx[4] = {64, 64, 1, 1};
+      AF2_TRY(make_tmap(&ta, c.A, 4, da, sa, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+      unsigned long long db[4] = {(unsigned long long)c.N, (unsigned long long)c.K, 2ull, (unsigned long long)c.batch};
+      unsigned long long sb[3] = {(unsigned long long)c.ldb * 2, (unsigned long long)c.b_half * 2, bb_ ? bb_ : (unsigned long long)c.b_half * 4};
+      AF2_TRY(make_tmap(&tb, c.Bm, 4, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+  } else if (!c.mn_major) {
     unsigned long long da[3] = {(unsigned long long)c.K, (unsigned long long)c.M, (unsigned long long)c.batch};
     unsigned long long sa[2] = {(unsigned long long)c.lda * 2, (unsigned long long)(c.batch > 1 ? c.a_batch : c.lda * c.M) * 2};
     unsigned ba[3] = {64, 128, 1};
@@ -214,7 +239,7 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = c.M; p.N = c.N; p.K = c.K; p.batch = c.batch;
+  p.M = c.M; p.N = c.N; p.K = c.K; p.batch = c.batch; p.nseg = c.nseg > 1 ? c.nseg : 1;
   p.num_ntiles = (c.N + BN - 1) / BN;
   p.out_cols = c.out_cols > 0 ? c.out_cols : ((c.mode == EPI_GATED_BF16) ? c.N / 2 : c.N);
   p.rowscale = c.rowscale; p.resid = c.resid; p.ld_resid = c.ld_resid;
@@ -644,7 +669,7 @@ long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads
 
 static int axial_attention_impl(const af2_attn_weights* w, float* x, const float* edges, const void* pre_bias,
                                 const unsigned char* mask, int B, int h, int wdim, int d, int heads, int dim_head,
-                                int row_attn, void* workspace, long long workspace_bytes, af2_stream_t stream) {
+                                int row_attn, void* workspace, long long workspace_bytes, af2_stream_t stream, int tied = 0) {
   NvtxRange nvtx_(row_attn ? "af2_axial_attention(row)" : "af2_axial_attention(col)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!w || !x) return fail(AF2_ERR_BAD_ARG, "axial_attention: null argument");
@@ -723,6 +748,11 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   const long long tok_sb = row_attn ? wdim : 1, tok_si = row_attn ? 1 : wdim;
   for (int b = 0; b < B; ++b) {
     const long long t0 = (long long)b * h * wdim;
+    if (tied) {   // MSAColumnGlobalAttention-style tied queries (alphafold2.py:142-151): q <- mean over the folded batch
+      ProfScope ps(s, KC_MISC, 0.0, 0.0);
+      tie_queries_kernel<__nv_bfloat16><<<ew_grid((long long)n * I), 256, 0, s>>>(qkv + t0 * 3 * I, 3 * I, (int)I, n, nb, tok_sb, tok_si);
+      CUDA_OK(cudaGetLastError());
+    }
     AF2_TRY(launch_attention(qkv + t0 * 3 * I, heads, dim_head, n, nb, tok_sb, tok_si,
                              has_bias ? bias + (long long)b * heads * n * npad : nullptr, npad,
                              mask ? mask + t0 : nullptr, gate + t0 * I, og + t0 * I, s));
@@ -910,6 +940,14 @@ int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges,
                         long long workspace_bytes, af2_stream_t stream) {
   return axial_attention_impl(w, x, edges, nullptr, mask, B, h, wdim, d, heads, dim_head, row_attn, workspace,
                               workspace_bytes, stream);
+}
+
+// same with flags: bit 0 = tied queries (global_query_attn of the extra-MSA stack, alphafold2.py:142-151, 250)
+int af2_axial_attention_ex(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask, int B,
+                           int h, int wdim, int d, int heads, int dim_head, int row_attn, int flags, void* workspace,
+                           long long workspace_bytes, af2_stream_t stream) {
+  return axial_attention_impl(w, x, edges, nullptr, mask, B, h, wdim, d, heads, dim_head, row_attn, workspace,
+                              workspace_bytes, stream, flags & 1);
 }
 
 int af2_axial_attention_prebias(const af2_attn_weights* w, float* x, const void* bias_bf16, const unsigned char* mask,
@@ -1171,3 +1209,5 @@ int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const voi
 }
 
 }  // extern "C"
+
+#include "strict_api.inl"

@@ -54,6 +54,11 @@ struct GemmParams {
   long long ld_resid;
   long long out_batch_stride;  // elements
   int cm_inner, cm_pitch;      // channel-major: row r -> (r / cm_inner) * cm_pitch + r % cm_inner
+  // Split-bf16 ("bf16x3", strict precision) operands: every fp32 operand value v is stored as two bf16 planes hi = bf16(v),
+  // lo = bf16(v - hi) (tensor maps of rank 4: k, row, plane, batch) and the k loop runs nseg = 3 passes over K with the
+  // plane pairs (A, B) = (hi, lo), (lo, hi), (hi, hi): C = A_hi B_lo + A_lo B_hi + A_hi B_hi in the fp32 accumulator, i.e.
+  // ~16 mantissa bits per operand (the dropped lo x lo term is 2^-18 relative).  nseg = 1: plain bf16 operands, rank-3 maps.
+  int nseg;
   NTile tile;
 };
 
@@ -198,6 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = p.num_ntiles;
   const int total_tiles = p.batch * m_tiles * n_tiles;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int nseg = p.nseg > 1 ? p.nseg : 1;
+  const int num_kk = num_kb * nseg;                 // k-blocks the MMA warp consumes per tile
 
   // epilogue geometry shared by the staging producer (warp 3) and the epilogue warps
   const int e_mode = (EK == EK_GENERIC) ? p.tile.mode : EpiTraits<EK>::mode;
@@ -216,12 +223,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt = tile % n_tiles;
         const int mt = (tile / n_tiles) % m_tiles;
         const int b = tile / (n_tiles * m_tiles);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kk = 0; kk < num_kb * nseg; ++kk) {
+          const int seg = kk / num_kb, kb = kk - seg * num_kb;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if constexpr (!MN_MAJOR) {
+          if (nseg > 1) {
+            // split operands (rank-4 maps): small cross terms first, hi x hi last
+            const int ha = (seg == 1) ? 1 : 0, hb = (seg == 0) ? 1 : 0;
+            if constexpr (!MN_MAJOR) {
+              tma_load_4d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM, ha, b);
+              tma_load_4d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN, hb, b);
+            } else {
+#pragma unroll
+              for (int h = 0; h < GEMM_BM / 64; ++h)
+                tma_load_4d(sa + h * 8192, &tmA, &full_bar[stage], mt * GEMM_BM + h * 64, kb * GEMM_BK, ha, b);
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_4d(sb + h * 8192, &tmB, &full_bar[stage], nt * BN + h * 64, kb * GEMM_BK, hb, b);
+            }
+          } else if constexpr (!MN_MAJOR) {
             tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM, b);
             tma_load_3d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN, b);
           } else {
@@ -249,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kk; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -270,7 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          if (kb == num_kk - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -477,6 +477,34 @@ __global__ void __launch_bounds__(256) outer_scale_bits_kernel(const uint8_t* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tied ("global") queries of the extra-MSA stack (alphafold2.py:142-151): q[b'][i][:] <- mean over the folded batch b' of
+// q[b'][i][:] (plain mean, the mask plays no role), written back over every b'.  buf row of token(b', i) = b'*tok_sb + i*tok_si
+// has ld elements; the first `cols` of them are the (already scaled) queries.  T = float (strict mode) or bf16.
+// ------------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ float tie_ld(const T* p);
+template <> __device__ __forceinline__ float tie_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float tie_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <class T> __device__ __forceinline__ void tie_st(T* p, float v);
+template <> __device__ __forceinline__ void tie_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void tie_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <class T>
+__global__ void __launch_bounds__(256) tie_queries_kernel(T* __restrict__ buf, long long ld, int cols, int n, int nbatch,
+                                                          long long tok_sb, long long tok_si) {
+  const long long total = static_cast<long long>(n) * cols;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % cols);
+    const long long i = idx / cols;
+    T* base = buf + i * tok_si * ld + c;
+    float acc = 0.f;
+    for (int b = 0; b < nbatch; ++b) acc += tie_ld<T>(base + b * tok_sb * ld);
+    const float mean = acc / static_cast<float>(nbatch);
+    for (int b = 0; b < nbatch; ++b) tie_st<T>(base + b * tok_sb * ld, mean);
+  }
+}
+
 // bool mask -> float 0/1 row scale
 __global__ void mask_to_float_kernel(const uint8_t* __restrict__ mask, float* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;

@@ -186,9 +186,10 @@ def _p(t):
 class Packed:
     """Keeps the packed tensors alive next to the ctypes struct that points at them."""
 
-    def __init__(self, struct, tensors):
+    def __init__(self, struct, tensors, kind: str = "bf16"):
         self.struct = struct
         self.tensors = tensors
+        self.kind = kind          # "bf16" (default path) or "strict" (split-bf16 x3 operands)
 
 
 def pack_feed_forward(norm_w, norm_b, w1, b1, w2, b2) -> Packed:
@@ -257,6 +258,61 @@ def pack_outer_mean(norm_w, norm_b, wl, bl, wr, br, wo, bo) -> Packed:
 
 
 # --------------------------------------------------------------------------------------------------
+# strict precision mode: split-bf16 weights (v = hi + lo), fp32 biases / LayerNorm affine
+# --------------------------------------------------------------------------------------------------
+def split_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 [rows, 2, align8(K)]: plane 0 = bf16(w), plane 1 = bf16(w - plane 0); pad columns zero."""
+    w = w.detach().to(torch.float32)
+    rows, K = w.shape
+    P = (K + 7) // 8 * 8
+    out = torch.zeros(rows, 2, P, dtype=torch.bfloat16, device=w.device)
+    hi = w.to(torch.bfloat16)
+    out[:, 0, :K] = hi
+    out[:, 1, :K] = (w - hi.float()).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def _bias_pad(b: torch.Tensor) -> torch.Tensor:
+    """fp32 bias zero-padded to a multiple of 256 entries: the GEMM epilogue loads biases per 32-column chunk of a 256-column tile."""
+    return _pad_rows(b.detach().to(torch.float32).reshape(-1)).contiguous()
+
+
+def pack_feed_forward_strict(norm_w, norm_b, w1, b1, w2, b2) -> Packed:
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), w1=split_weight(w1), b1=_bias_pad(b1), w2=split_weight(w2), b2=_bias_pad(b2))
+    s = _lib.FFWeightsStrict(*(t[k].data_ptr() for k in ("g", "b", "w1", "b1", "w2", "b2")))
+    pk = Packed(s, t, "strict")
+    pk.hidden = int(w2.shape[1])
+    return pk
+
+
+def pack_attention_strict(norm_w, norm_b, wq, wkv, wg, bg, wo, bo, w_edge, dim_head: int) -> Packed:
+    wcat = torch.cat([wq.detach().float() * dim_head ** -0.5, wkv.detach().float(), wg.detach().float()], 0)   # alphafold2.py:138
+    bcat = torch.cat([torch.zeros(wq.shape[0] + wkv.shape[0], device=wq.device), bg.detach().float()], 0)
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), w=split_weight(wcat), bias=_bias_pad(bcat), wo=split_weight(wo), bo=_bias_pad(bo))
+    if w_edge is not None:
+        t["we"] = _f32(w_edge)
+    s = _lib.AttnWeightsStrict(t["g"].data_ptr(), t["b"].data_ptr(), t["w"].data_ptr(), t["bias"].data_ptr(), t["wo"].data_ptr(),
+                               t["bo"].data_ptr(), _p(t.get("we")))
+    return Packed(s, t, "strict")
+
+
+def pack_triangle_multiply_strict(norm_w, norm_b, wl, bl, wr, br, wlg, blg, wrg, brg, wog, bog, onw, onb, wo, bo) -> Packed:
+    f = lambda x: x.detach().float()  # noqa: E731
+    w5 = torch.cat([f(wl), f(wr), f(wlg), f(wrg), f(wog)], 0)
+    b5 = torch.cat([f(bl), f(br), f(blg), f(brg), f(bog)], 0)
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), w5=split_weight(w5), b5=_bias_pad(b5), ong=_f32(onw), onb=_f32(onb), wo=split_weight(wo), bo=_bias_pad(bo))
+    s = _lib.TriMulWeightsStrict(*(t[k].data_ptr() for k in ("g", "b", "w5", "b5", "ong", "onb", "wo", "bo")))
+    return Packed(s, t, "strict")
+
+
+def pack_outer_mean_strict(norm_w, norm_b, wl, bl, wr, br, wo, bo) -> Packed:
+    t = dict(g=_f32(norm_w), b=_f32(norm_b), wlr=split_weight(torch.cat([wl.detach().float(), wr.detach().float()], 0)),
+             blr=_bias_pad(torch.cat([bl.detach(), br.detach()], 0)), wo=split_weight(wo), bo=_bias_pad(bo))
+    s = _lib.OuterWeightsStrict(*(t[k].data_ptr() for k in ("g", "b", "wlr", "blr", "wo", "bo")))
+    return Packed(s, t, "strict")
+
+
+# --------------------------------------------------------------------------------------------------
 # ops (all in place on the fp32 residual stream)
 # --------------------------------------------------------------------------------------------------
 def feed_forward_(pk: Packed, x: torch.Tensor) -> torch.Tensor:
@@ -265,6 +321,12 @@ def feed_forward_(pk: Packed, x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     d = x.shape[-1]
     tokens = x.numel() // d
+    if pk.kind == "strict":
+        hidden = pk.hidden
+        ws = workspace(lib.af2_feed_forward_strict_workspace(tokens, d, hidden), x.device)
+        _lib.check(lib.af2_feed_forward_strict(C.byref(pk.struct), x.data_ptr(), tokens, d, hidden, ws.data_ptr(), ws.numel(),
+                                               _stream_ptr()))
+        return x
     hidden = pk.tensors["w2"].shape[1]
     nbytes = lib.af2_feed_forward_workspace(tokens, d, hidden)
     ws = workspace(nbytes, x.device)
@@ -274,8 +336,9 @@ def feed_forward_(pk: Packed, x: torch.Tensor) -> torch.Tensor:
 
 
 def axial_attention_(pk: Packed, x: torch.Tensor, heads: int, dim_head: int, row_attn: bool,
-                     edges: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [b, h, w, d] fp32  <-  x + AxialAttention(x, edges, mask)   (alphafold2.py:192-255, 98-190)."""
+                     edges: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, tied: bool = False) -> torch.Tensor:
+    """x [b, h, w, d] fp32  <-  x + AxialAttention(x, edges, mask)   (alphafold2.py:192-255, 98-190).
+    tied: global_query_attn -- queries averaged over the folded axis (alphafold2.py:142-151, 250)."""
     _require(x, torch.float32, "x")
     if x.dim() != 4:
         raise ValueError("x must be [b, h, w, d]")
@@ -289,10 +352,15 @@ def axial_attention_(pk: Packed, x: torch.Tensor, heads: int, dim_head: int, row
             edges = None                      # module built without accept_edges: the reference ignores edges
     mask = _mask_u8(mask, (B, h, w), "mask")
     lib = _lib.load()
+    if pk.kind == "strict":
+        ws = workspace(lib.af2_axial_attention_strict_workspace(B, h, w, d, heads, dim_head, int(row_attn)), x.device)
+        _lib.check(lib.af2_axial_attention_strict(C.byref(pk.struct), x.data_ptr(), _ptr(edges), _ptr(mask), B, h, w, d, heads,
+                                                  dim_head, int(row_attn), int(tied), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        return x
     nbytes = lib.af2_axial_attention_workspace(B, h, w, d, heads, dim_head, int(row_attn))
     ws = workspace(nbytes, x.device)
-    _lib.check(lib.af2_axial_attention(C.byref(pk.struct), x.data_ptr(), _ptr(edges), _ptr(mask), B, h, w, d, heads,
-                                       dim_head, int(row_attn), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    _lib.check(lib.af2_axial_attention_ex(C.byref(pk.struct), x.data_ptr(), _ptr(edges), _ptr(mask), B, h, w, d, heads,
+                                          dim_head, int(row_attn), int(tied), ws.data_ptr(), ws.numel(), _stream_ptr()))
     return x
 
 
@@ -303,6 +371,11 @@ def triangle_multiply_(pk: Packed, x: torch.Tensor, ingoing: bool, mask: Optiona
     B, N, _, d = x.shape
     mask = _mask_u8(mask, (B, N, N), "mask")
     lib = _lib.load()
+    if pk.kind == "strict":
+        ws = workspace(lib.af2_triangle_multiply_strict_workspace(B, N, d), x.device)
+        _lib.check(lib.af2_triangle_multiply_strict(C.byref(pk.struct), x.data_ptr(), _ptr(mask), B, N, d, int(ingoing),
+                                                    ws.data_ptr(), ws.numel(), _stream_ptr()))
+        return x
     nbytes = lib.af2_triangle_multiply_workspace(B, N, d)
     ws = workspace(nbytes, x.device)
     _lib.check(lib.af2_triangle_multiply(C.byref(pk.struct), x.data_ptr(), _ptr(mask), B, N, d, int(ingoing),
@@ -320,6 +393,11 @@ def outer_mean_(pk: Packed, x: torch.Tensor, m: torch.Tensor, msa_mask: Optional
         raise ValueError(f"x must be [{B}, {N}, {N}, {d}], got {tuple(x.shape)}")
     msa_mask = _mask_u8(msa_mask, (B, S, N), "msa_mask")
     lib = _lib.load()
+    if pk.kind == "strict":
+        ws = workspace(lib.af2_outer_mean_strict_workspace(B, S, N, d), x.device)
+        _lib.check(lib.af2_outer_mean_strict(C.byref(pk.struct), x.data_ptr(), m.data_ptr(), _ptr(msa_mask), B, S, N, d,
+                                             float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()))
+        return x
     nbytes = lib.af2_outer_mean_workspace(B, S, N, d)
     ws = workspace(nbytes, x.device)
     _lib.check(lib.af2_outer_mean(C.byref(pk.struct), x.data_ptr(), m.data_ptr(), _ptr(msa_mask), B, S, N, d,
@@ -340,6 +418,55 @@ def apply_rotary_pos_emb(x: torch.Tensor, sinu_pos) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# pre- / post-trunk glue
+# --------------------------------------------------------------------------------------------------
+def _w32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def embed_pair_init(seq, msa, token_emb, w_pair, b_pair, pos_emb, max_rel_dist: int, seq_embed=None, msa_embed=None, seq_index=None):
+    """alphafold2.py:676-726 in three fused kernels: returns (x [b,n,n,d], m [b,s,n,d]) fp32."""
+    if not seq.is_cuda:
+        raise RuntimeError("seq must be a CUDA tensor (alphafold2_b200 has no CPU fallback)")
+    emb = _w32(token_emb)
+    _require(emb, torch.float32, "token_emb.weight")
+    B, n = seq.shape
+    S = msa.shape[1]
+    d = emb.shape[1]
+    seq = seq.to(torch.int64).contiguous()
+    msa = msa.to(torch.int64).contiguous()
+    x = torch.empty(B, n, n, d, dtype=torch.float32, device=seq.device)
+    m = torch.empty(B, S, n, d, dtype=torch.float32, device=seq.device)
+    se = None if seq_embed is None else _w32(seq_embed)
+    me = None if msa_embed is None else _w32(msa_embed)
+    si = None if seq_index is None else seq_index.to(device=seq.device, dtype=torch.int64).contiguous()
+    lib = _lib.load()
+    ws = workspace(lib.af2_embed_pair_init_workspace(B, n, d), seq.device)
+    wp, bp, pe = _w32(w_pair), _w32(b_pair), _w32(pos_emb)
+    _lib.check(lib.af2_embed_pair_init(seq.data_ptr(), msa.data_ptr(), emb.data_ptr(), emb.shape[0], _ptr(se), _ptr(me), wp.data_ptr(),
+                                       bp.data_ptr(), pe.data_ptr(), int(max_rel_dist), _ptr(si), x.data_ptr(), m.data_ptr(), B, S, n, d,
+                                       ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return x, m
+
+
+def distogram_head_ok(d: int, buckets: int) -> bool:
+    return d % 128 == 0 and d <= 512 and (buckets * d + buckets) * 4 <= 200 * 1024
+
+
+def distogram_head(x, ln_w, ln_b, w, b) -> torch.Tensor:
+    """alphafold2.py:821-823: Linear(LayerNorm((x + x^T) / 2)) -> [b, n, n, buckets] fp32, one fused kernel."""
+    _require(x, torch.float32, "x")
+    B, n, _, d = x.shape
+    buckets = w.shape[0]
+    out = torch.empty(B, n, n, buckets, dtype=torch.float32, device=x.device)
+    g, be, ww, bb = _w32(ln_w), _w32(ln_b), _w32(w), _w32(b)
+    _lib.check(_lib.load().af2_distogram_head(x.data_ptr(), g.data_ptr(), be.data_ptr(), ww.data_ptr(), bb.data_ptr(), out.data_ptr(),
+                                              B, n, d, buckets, _stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # building blocks exported for the parity tests
 # --------------------------------------------------------------------------------------------------
 def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
@@ -349,6 +476,25 @@ def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps
     _lib.check(_lib.load().af2_layernorm_bf16(x.data_ptr(), _f32(gamma).data_ptr(), _f32(beta).data_ptr(), y.data_ptr(),
                                               x.numel() // d, d, float(eps), _stream_ptr()))
     return y
+
+
+def gemm_split(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Strict-mode building block: a [batch, M, K] x b [batch, N, K] fp32 -> [batch, M, N] fp32 through split-bf16 operands
+    (three tensor-core passes, fp32 accumulate)."""
+    _require(a, torch.float32, "a")
+    _require(b, torch.float32, "b")
+    batch, M, K = a.shape
+    N = b.shape[1]
+    P = (K + 7) // 8 * 8
+    lib = _lib.load()
+    a_s = torch.empty(batch * M, 2, P, dtype=torch.bfloat16, device=a.device)
+    b_s = torch.empty(batch * N, 2, P, dtype=torch.bfloat16, device=a.device)
+    _lib.check(lib.af2_split_bf16(a.data_ptr(), a_s.data_ptr(), batch * M, K, _stream_ptr()))
+    _lib.check(lib.af2_split_bf16(b.data_ptr(), b_s.data_ptr(), batch * N, K, _stream_ptr()))
+    ldc = (N + 3) // 4 * 4
+    c = torch.empty(batch, M, ldc, dtype=torch.float32, device=a.device)
+    _lib.check(lib.af2_gemm_split_f32(a_s.data_ptr(), b_s.data_ptr(), c.data_ptr(), ldc, M, N, K, batch, _stream_ptr()))
+    return c[:, :, :N]
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, mn_major: bool = False) -> torch.Tensor:

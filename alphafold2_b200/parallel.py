@@ -157,6 +157,8 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
     x [1, N, N, d], m [1, S, N, d], mask [1, N, N] bool, msa_mask [1, S, N] bool are the full (replicated) inputs;
     returns the full (x, m) on every rank when gather_output, else this rank's row shards.
     """
+    if stage_ops is None and _ops.precision_of(evo) == "strict":
+        raise NotImplementedError("the strict precision mode runs on one GPU (it is a parity mode, not a throughput mode)")
     ops = stage_ops if stage_ops is not None else CudaStageOps()
     P = dist.get_world_size(group)
     r = dist.get_rank(group)

@@ -83,6 +83,11 @@ typedef struct {
 int af2_axial_attention(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask,
                         int B, int h, int wdim, int d, int heads, int dim_head, int row_attn,
                         void* workspace, long long workspace_bytes, af2_stream_t stream);
+/* af2_axial_attention with flags: bit 0 = tied ("global") queries -- the queries are averaged over the folded batch before
+ * the dot products (alphafold2.py:142-151; AxialAttention(global_query_attn=True), :250; used by the extra-MSA stack :518-527) */
+int af2_axial_attention_ex(const af2_attn_weights* w, float* x, const float* edges, const unsigned char* mask, int B,
+                           int h, int wdim, int d, int heads, int dim_head, int row_attn, int flags, void* workspace,
+                           long long workspace_bytes, af2_stream_t stream);
 long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads, int dim_head, int row_attn);
 
 /* ---------------- TriangleMultiplicativeModule: alphafold2.py:257-317 (+ residual :381-382) ----------
@@ -169,6 +174,69 @@ int af2_layernorm_bf16(const float* x, const float* gamma, const float* beta, vo
 int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const void* Bm, long long ldb,
                       long long b_batch, float* C, long long ldc, long long c_batch, int M, int N, int K,
                       int batch, int mn_major, af2_stream_t stream);
+
+/* ======================================================================================================================
+ * STRICT precision mode (alphafold2_b200.set_precision(model, "strict")): the same modules with fp32 activations between
+ * kernels and split-bf16 operands on the tensor cores (v = hi + lo; hi*lo + lo*hi + hi*hi accumulated in fp32, ~16
+ * mantissa bits per operand), so that results match the reference's fp32 path inside the north star's rtol 1e-3 /
+ * atol 1e-4.  Split weights: bf16 [rows][2][align8(cols)] (hi plane | lo plane per row), built by ops.split_weight().
+ * ====================================================================================================================== */
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* FeedForward.norm                                   */
+  const void* w1; const float* b1;                    /* net.0  split [2*hid][2][align8(d)], fp32 [2*hid]    */
+  const void* w2; const float* b2;                    /* net.3  split [d][2][align8(hid)],   fp32 [d]        */
+} af2_ff_weights_strict;
+long long af2_feed_forward_strict_workspace(long long tokens, int d, int hidden);
+int af2_feed_forward_strict(const af2_ff_weights_strict* w, float* x, long long tokens, int d, int hidden, void* workspace,
+                            long long workspace_bytes, af2_stream_t stream);                 /* alphafold2.py:74-94 */
+
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* AxialAttention.norm                                              */
+  const void* w_qkvg; const float* b_qkvg;            /* [to_q * dim_head^-0.5 ; to_kv ; gating] split [4I][2][align8(d)], bias [4I] (zeros | gating.bias) */
+  const void* w_out; const float* b_out;              /* attn.to_out split [d][2][align8(I)], fp32 [d]                    */
+  const float* w_edge;                                /* edges_to_attn_bias.0.weight fp32 [H][d] or NULL                  */
+} af2_attn_weights_strict;
+long long af2_axial_attention_strict_workspace(int B, int h, int w, int d, int heads, int dim_head, int row_attn);
+int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const float* edges, const unsigned char* mask, int B,
+                               int h, int wdim, int d, int heads, int dim_head, int row_attn, int flags, void* workspace,
+                               long long workspace_bytes, af2_stream_t stream);              /* alphafold2.py:98-255; flags as af2_axial_attention_ex */
+
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* norm                                                                          */
+  const void* w5; const float* b5;                    /* [left_proj; right_proj; left_gate; right_gate; out_gate] split [5d][2][align8(d)], fp32 [5d] */
+  const float* on_gamma; const float* on_beta;        /* to_out_norm                                                                   */
+  const void* w_out; const float* b_out;              /* to_out split [d][2][align8(d)], fp32 [d]                                      */
+} af2_trimul_weights_strict;
+long long af2_triangle_multiply_strict_workspace(int B, int N, int d);
+int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, const unsigned char* mask, int B, int N, int d,
+                                 int ingoing, void* workspace, long long workspace_bytes, af2_stream_t stream);   /* alphafold2.py:257-317 */
+
+typedef struct {
+  const float* ln_gamma; const float* ln_beta;        /* norm                                                       */
+  const void* w_lr; const float* b_lr;                /* [left_proj; right_proj] split [2d][2][align8(d)], fp32 [2d] */
+  const void* w_out; const float* b_out;              /* proj_out split [d][2][align8(d)], fp32 [d]                 */
+} af2_outer_weights_strict;
+long long af2_outer_mean_strict_workspace(int B, int S, int N, int d);
+int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
+                          int N, int d, float eps, void* workspace, long long workspace_bytes, af2_stream_t stream);   /* alphafold2.py:321-351 */
+
+/* building blocks exported for the parity tests of the split-operand GEMM */
+int af2_split_bf16(const float* x, void* y_split, long long rows, int K, af2_stream_t stream);
+int af2_gemm_split_f32(const void* A_split, const void* B_split, float* C, long long ldc, int M, int N, int K, int batch,
+                       af2_stream_t stream);
+
+/* ---------------- pre- / post-trunk glue as fused kernels -------------------------------------------
+ * af2_embed_pair_init: alphafold2.py:676-726 -- token embedding gather, m = (emb[msa] + msa_embed) + emb[seq],
+ *   x[i][j] = (left[i] + right[j]) + pos_emb[clamp(idx_i - idx_j, -R, R) + R] with [left|right] = to_pairwise_repr(emb[seq] + seq_embed).
+ *   seq [B][n], msa [B][S][n] int64 token ids (msa / m may be NULL); seq_embed, msa_embed, seq_index optional (NULL).
+ * af2_distogram_head: alphafold2.py:821-823 -- out = Linear_{d -> buckets}(LayerNorm((x + x^T) / 2)), all fp32. */
+long long af2_embed_pair_init_workspace(int B, int n, int d);
+int af2_embed_pair_init(const long long* seq, const long long* msa, const float* token_emb, int vocab, const float* seq_embed,
+                        const float* msa_embed, const float* w_pair, const float* b_pair, const float* pos_emb, int max_rel_dist,
+                        const long long* seq_index, float* x, float* m, int B, int S, int n, int d, void* workspace,
+                        long long workspace_bytes, af2_stream_t stream);
+int af2_distogram_head(const float* x, const float* gamma, const float* beta, const float* w, const float* bias, float* out, int B,
+                       int n, int d, int buckets, af2_stream_t stream);
 
 #ifdef __cplusplus
 }

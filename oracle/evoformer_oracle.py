@@ -219,19 +219,20 @@ def msa_attention_block(w: W, p: str, m: Tensor, heads: int, mask=None, pairwise
 
 
 def evoformer_block(w: W, p: str, x: Tensor, m: Tensor, heads: int, mask=None, msa_mask=None,
-                    literal_outer: bool = False, chunk: int = 0):
-    """Order (alphafold2.py:438-444): MSA attn -> MSA FF -> pair block (updated m) -> pair FF."""
+                    literal_outer: bool = False, chunk: int = 0, global_column_attn: bool = False):
+    """Order (alphafold2.py:438-444): MSA attn -> MSA FF -> pair block (updated m) -> pair FF.
+    global_column_attn (alphafold2.py:367, 421): the pair block's ingoing triangle attention ties its queries."""
     m = msa_attention_block(w, p + "layer.2.", m, heads, msa_mask, x, chunk)
     m = feed_forward(w, p + "layer.3.", m) + m
-    x = pairwise_attention_block(w, p + "layer.0.", x, heads, mask, m, msa_mask, literal_outer, chunk)
+    x = pairwise_attention_block(w, p + "layer.0.", x, heads, mask, m, msa_mask, literal_outer, chunk, global_column_attn)
     x = feed_forward(w, p + "layer.1.", x) + x
     return x, m
 
 
 def evoformer(w: W, p: str, x: Tensor, m: Tensor, heads: int, depth: int, mask=None, msa_mask=None,
-              literal_outer: bool = False, chunk: int = 0):
+              literal_outer: bool = False, chunk: int = 0, global_column_attn: bool = False):
     for l in range(depth):
-        x, m = evoformer_block(w, f"{p}layers.{l}.", x, m, heads, mask, msa_mask, literal_outer, chunk)
+        x, m = evoformer_block(w, f"{p}layers.{l}.", x, m, heads, mask, msa_mask, literal_outer, chunk, global_column_attn)
     return x, m
 
 
@@ -241,8 +242,10 @@ def evoformer(w: W, p: str, x: Tensor, m: Tensor, heads: int, depth: int, mask=N
 def alphafold2_distogram(w: W, seq: Tensor, msa: Optional[Tensor], mask: Optional[Tensor],
                          msa_mask: Optional[Tensor], heads: int, depth: int, max_rel_dist: int = 32,
                          dtype=torch.float32, literal_outer: bool = False, chunk: int = 0,
-                         return_trunk: bool = False):
-    """seq [b,n] int64, msa [b,s,n] int64, mask [b,n] bool, msa_mask [b,s,n] bool -> distance logits."""
+                         return_trunk: bool = False, extra_msa_mask: Optional[Tensor] = None, extra_depth: int = 0):
+    """seq [b,n] int64, msa [b,s,n] int64, mask [b,n] bool, msa_mask [b,s,n] bool -> distance logits.
+    extra_depth > 0: the extra-MSA stack of alphafold2.py:789-798 runs first, exactly as the reference does (quirk Q11: it
+    embeds `msa` again, keeps only the pair output; its blocks use global_column_attn, alphafold2.py:518-527)."""
     if msa is None:                                                         # alphafold2.py:656-658
         msa = seq[:, None, :]
         msa_mask = mask[:, None, :]
@@ -259,6 +262,10 @@ def alphafold2_distogram(w: W, seq: Tensor, msa: Optional[Tensor], mask: Optiona
     idx = torch.arange(n, device=seq.device)
     rel = (idx[:, None] - idx[None, :]).clamp(-max_rel_dist, max_rel_dist) + max_rel_dist
     x = x + w["pos_emb.weight"].to(dtype)[rel][None]
+    if extra_depth > 0:
+        extra_m = emb[msa]                                                    # alphafold2.py:790 (sic: msa, not extra_msa)
+        x, _ = evoformer(w, "extra_msa_evoformer.", x, extra_m, heads, extra_depth, x_mask, extra_msa_mask, literal_outer, chunk,
+                         global_column_attn=True)
     x, m = evoformer(w, "net.", x, m, heads, depth, x_mask, msa_mask, literal_outer, chunk)
     if return_trunk:
         return x, m

@@ -135,3 +135,31 @@ def test_quirk_masked_query_uniform():
 
 def test_flops_formula():
     assert abs(O.evoformer_flops_per_block(256, 128, 256, 8, 64) / 1e9 - 649.3) < 0.5
+
+
+def test_evoformer_global_column_attn():
+    """n2: tied-query ("global") ingoing triangle attention of the extra-MSA stack (alphafold2.py:142-151, 250, 367)."""
+    fx = load_golden("evoformer_global_col")
+    i, c = fx["inputs"], fx["cfg"]
+    x, m = O.evoformer(fx["state"], "", i["x"], i["m"], c["heads"], 1, i["mask"], i["msa_mask"], global_column_attn=True)
+    torch.testing.assert_close(x, fx["out_fp32"][0], rtol=5e-4, atol=5e-5)
+    torch.testing.assert_close(m, fx["out_fp32"][1], rtol=5e-4, atol=5e-5)
+    x, m = O.evoformer(_to(fx["state"], torch.float64), "", i["x"].double(), i["m"].double(), c["heads"], 1, i["mask"], i["msa_mask"],
+                       global_column_attn=True)
+    torch.testing.assert_close(x, fx["out_fp64"][0], rtol=1e-6, atol=1e-7)
+    # the tie really matters: the untied block gives a different pair tensor
+    xu, _ = O.evoformer(fx["state"], "", i["x"], i["m"], c["heads"], 1, i["mask"], i["msa_mask"])
+    assert (xu - fx["out_fp32"][0]).abs().max() > 1e-3
+
+
+def test_alphafold2_extra_msa():
+    """n2: Alphafold2.forward with extra_msa / extra_msa_mask (alphafold2.py:789-798, quirk Q11 included)."""
+    fx = load_golden("alphafold2_extra_msa")
+    i, cfg = fx["inputs"], fx["cfg"]
+    out = O.alphafold2_distogram(fx["state"], i["seq"], i["msa"], i["mask"], i["msa_mask"], cfg["heads"], cfg["depth"],
+                                 extra_msa_mask=i["extra_msa_mask"], extra_depth=cfg["extra_msa_evoformer_layers"])
+    torch.testing.assert_close(out, fx["out_fp32"], rtol=5e-4, atol=5e-5)
+    out = O.alphafold2_distogram(_to(fx["state"], torch.float64), i["seq"], i["msa"], i["mask"], i["msa_mask"], cfg["heads"],
+                                 cfg["depth"], dtype=torch.float64, extra_msa_mask=i["extra_msa_mask"],
+                                 extra_depth=cfg["extra_msa_evoformer_layers"])
+    torch.testing.assert_close(out, fx["out_fp64"], rtol=1e-6, atol=1e-7)
