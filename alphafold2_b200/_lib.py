@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libaf2b200.so")
+# AF2_LIB_PATH: A/B builds of the same library on one box (tools/gpu_ab.sh); never a different implementation
+LIB_PATH = os.environ.get("AF2_LIB_PATH") or os.path.join(_HERE, "csrc", "libaf2b200.so")
 
 _lib = None
 

@@ -168,6 +168,8 @@ struct GemmCall {
   int out_cols;           // 0: N (N/2 for GATED); else explicit number of valid output columns
   // split-bf16 operands (strict precision, GemmParams::nseg): nseg = 3, a_half / b_half = element stride between the hi and lo planes
   int nseg; long long a_half, b_half;
+  // gathered operands (GemmParams::a_pr / b_pr): rows (K-major) or columns (MN-major) per piece, element stride between pieces
+  int a_pr, b_pr; long long a_piece, b_piece;
 };
 
 template <int BN, int STAGES, bool MN, int EK>
@@ -237,9 +239,44 @@ int launch_gemm(const GemmCall& c, cudaStream_t s) {
     unsigned long long sb[2] = {(unsigned long long)c.ldb * 2, (unsigned long long)(c.batch > 1 ? c.b_batch : c.ldb * c.K) * 2};
     AF2_TRY(make_tmap(&tb, c.Bm, 3, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B));
   }
+  // gathered ("pieces") operands: replace the plain map by a rank-4 map (k | mn, row | k, piece, batch)
+  if (c.nseg <= 1 && (c.a_pr > 0 || c.b_pr > 0)) {
+    const unsigned long long bsa = (unsigned long long)(c.batch > 1 ? c.a_batch : c.lda) * 2, bsb = (unsigned long long)(c.batch > 1 ? c.b_batch : c.ldb) * 2;
+    if (!c.mn_major) {
+      if (c.a_pr > 0) {
+        if (c.a_pr % 128 != 0) return fail(AF2_ERR_BAD_ARG, "gemm: gathered A pieces of %d rows (need a multiple of 128)", c.a_pr);
+        unsigned long long da[4] = {(unsigned long long)c.K, (unsigned long long)c.a_pr, (unsigned long long)((c.M + c.a_pr - 1) / c.a_pr), (unsigned long long)c.batch};
+        unsigned long long sa[3] = {(unsigned long long)c.lda * 2, (unsigned long long)c.a_piece * 2, bsa};
+        unsigned ba[4] = {64, 128, 1, 1};
+        AF2_TRY(make_tmap(&ta, c.A, 4, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B));
+      }
+      if (c.b_pr > 0) {
+        if (!((c.b_pr % BN) == 0 || (BN % c.b_pr) == 0) || c.b_pr % 8) return fail(AF2_ERR_BAD_ARG, "gemm: gathered B pieces of %d rows do not tile BN=%d", c.b_pr, BN);
+        unsigned long long db[4] = {(unsigned long long)c.K, (unsigned long long)c.b_pr, (unsigned long long)((c.N + c.b_pr - 1) / c.b_pr), (unsigned long long)c.batch};
+        unsigned long long sb[3] = {(unsigned long long)c.ldb * 2, (unsigned long long)c.b_piece * 2, bsb};
+        unsigned bb[4] = {64, (unsigned)(c.b_pr >= BN ? BN : c.b_pr), (unsigned)(c.b_pr >= BN ? 1 : BN / c.b_pr), 1};
+        AF2_TRY(make_tmap(&tb, c.Bm, 4, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_128B));
+      }
+    } else {
+      unsigned bx[4] = {64, 64, 1, 1};
+      if (c.a_pr > 0) {
+        if (c.a_pr % 64) return fail(AF2_ERR_BAD_ARG, "gemm: gathered MN-major A pieces of %d columns (need a multiple of 64)", c.a_pr);
+        unsigned long long da[4] = {(unsigned long long)c.a_pr, (unsigned long long)c.K, (unsigned long long)((c.M + c.a_pr - 1) / c.a_pr), (unsigned long long)c.batch};
+        unsigned long long sa[3] = {(unsigned long long)c.lda * 2, (unsigned long long)c.a_piece * 2, bsa};
+        AF2_TRY(make_tmap(&ta, c.A, 4, da, sa, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+      }
+      if (c.b_pr > 0) {
+        if (c.b_pr % 64) return fail(AF2_ERR_BAD_ARG, "gemm: gathered MN-major B pieces of %d columns (need a multiple of 64)", c.b_pr);
+        unsigned long long db[4] = {(unsigned long long)c.b_pr, (unsigned long long)c.K, (unsigned long long)((c.N + c.b_pr - 1) / c.b_pr), (unsigned long long)c.batch};
+        unsigned long long sb[3] = {(unsigned long long)c.ldb * 2, (unsigned long long)c.b_piece * 2, bsb};
+        AF2_TRY(make_tmap(&tb, c.Bm, 4, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B));
+      }
+    }
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = c.M; p.N = c.N; p.K = c.K; p.batch = c.batch; p.nseg = c.nseg > 1 ? c.nseg : 1;
+  if (c.nseg <= 1) { p.a_pr = c.a_pr; p.b_pr = c.b_pr; }
   p.num_ntiles = (c.N + BN - 1) / BN;
   p.out_cols = c.out_cols > 0 ? c.out_cols : ((c.mode == EPI_GATED_BF16) ? c.N / 2 : c.N);
   p.rowscale = c.rowscale; p.resid = c.resid; p.ld_resid = c.ld_resid;
@@ -410,6 +447,8 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
+int g_attn_group = 1;     // 1: attention CTAs grouped per (h, b') unit for 2..8 query blocks (AF2_ATTN_GROUP=0: n > 256 ungrouped)
+int g_gather_fused = 1;   // 1: contractions over all-gathered operand pieces in ONE launch (AF2_GATHER_FUSED=0: one launch per piece)
 
 int launch_chan_to_token(const ChanLnParams& p, cudaStream_t s) {
   const long long T = (long long)p.rows * p.n;
@@ -464,9 +503,11 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured[cur_dev()] = true;
   }
-  const long long items = (long long)((p.n + 127) / 128) * p.heads * p.nbatch;
+  const int nqb = (p.n + 127) / 128;
+  const long long items = (long long)nqb * p.heads * p.nbatch;
   if (items <= 0) return AF2_OK;
-  const int grid = (int)(items < sm_count() ? items : sm_count());     // persistent CTAs
+  int grid = (int)(items < sm_count() ? items : sm_count());           // persistent CTAs
+  if (nqb >= 2 && nqb <= 8 && g_attn_group) grid = grid / nqb * nqb;    // groups of nqb CTAs share the K/V of their (h, b') units
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
@@ -601,6 +642,9 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_PROJ_PRODTILES")) g_proj_prod_tiles = atof(e);
   if (const char* e = getenv("AF2_PROJ_BALANCE")) g_proj_balance = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_WIDE")) g_proj_wide = atoi(e) != 0;
+  if (const char* e = getenv("AF2_PROJ_L2PF")) g_proj_l2pf = atoi(e) != 0;
+  if (const char* e = getenv("AF2_GATHER_FUSED")) g_gather_fused = atoi(e) != 0;
+  if (const char* e = getenv("AF2_ATTN_GROUP")) g_attn_group = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_TRACE")) {
     if (atoi(e) != 0 && !g_proj_trace) {
       if (cudaMalloc(&g_proj_trace, 2048 * sizeof(long long)) != cudaSuccess) g_proj_trace = nullptr;
@@ -1056,7 +1100,32 @@ int af2_triangle_contract(const af2_trimul_weights* w, float* x, const void* Lc,
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_contract: workspace too small");
   const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
   const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
-  for (int p = 0; p < pieces; ++p) {
+  // one launch over all gathered pieces when their size tiles the kernel's boxes (rank-4 tensor maps), else one per piece
+  bool fused_pieces = false;
+  if (pieces > 1 && g_gather_fused) {
+    GemmCall c;
+    memset(&c, 0, sizeof(c));
+    c.batch = d; c.K = K; c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.ld_out = cp4; c.out_batch = cs_o; c.out = Oc;
+    if (!ingoing) {
+      const int pc = cols / pieces, bn = pick_bn(cols);
+      if (pc % 8 == 0 && (pc % bn == 0 || bn % pc == 0)) {
+        c.A = L; c.lda = align_up(K, 8); c.a_batch = cs_l;
+        c.Bm = R; c.ldb = align_up(K, 8); c.b_batch = cs_r; c.b_pr = pc; c.b_piece = piece_stride;
+        c.mn_major = false; c.M = rows; c.N = cols; c.bn = bn;
+        fused_pieces = true;
+      }
+    } else {
+      const int pr = rows / pieces;
+      if (pr % 64 == 0) {
+        c.A = R; c.lda = align_up(pr, 8); c.a_batch = cs_r; c.a_pr = pr; c.a_piece = piece_stride;
+        c.Bm = L; c.ldb = align_up(cols, 8); c.b_batch = cs_l;
+        c.mn_major = true; c.M = rows; c.N = cols; c.bn = pick_bn(cols);
+        fused_pieces = true;
+      }
+    }
+    if (fused_pieces) AF2_TRY(launch_gemm(c, s));
+  }
+  for (int p = 0; p < pieces && !fused_pieces; ++p) {
     GemmCall c;
     memset(&c, 0, sizeof(c));
     c.batch = d; c.K = K; c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.ld_out = cp4; c.out_batch = cs_o;
@@ -1156,7 +1225,17 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
   const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
   const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
   const int pc = N / pieces;
-  for (int p = 0; p < pieces; ++p) {
+  const bool fused_pieces = pieces > 1 && g_gather_fused && pc % 64 == 0;
+  if (fused_pieces) {   // one launch: B columns j = p * pc + jj addressed through a rank-4 map over the gathered pieces
+    GemmCall g;
+    memset(&g, 0, sizeof(g));
+    g.A = L; g.lda = align_up(rows, 8); g.a_batch = cs_l;
+    g.Bm = R; g.ldb = align_up(pc, 8); g.b_batch = cs_r; g.b_pr = pc; g.b_piece = piece_stride;
+    g.mn_major = true; g.M = rows; g.N = N; g.K = S; g.batch = d; g.bn = pick_bn(N);
+    g.mode = EPI_STORE_F32; g.layout = LAYOUT_TOKEN; g.out = Oc; g.ld_out = np4; g.out_batch = cs_o;
+    AF2_TRY(launch_gemm(g, s));
+  }
+  for (int p = 0; p < pieces && !fused_pieces; ++p) {
     GemmCall g;
     memset(&g, 0, sizeof(g));
     g.A = L; g.lda = align_up(rows, 8); g.a_batch = cs_l;

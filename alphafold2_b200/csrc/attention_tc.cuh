@@ -113,7 +113,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* v_empty = bars + 18;   // [4] ... and consumed by the block's P V
   uint64_t* s_full = bars + 22;    // [2]
   uint64_t* p_full = bars + 24;    // [2] P of the block is in its S buffer
-  uint64_t* pv_done = bars + 26;
+  // (bars + 26 unused: the P V retirement is observed through v_empty)
   uint64_t* kb_full = bars + 27;   // [2] key-mask terms of a block staged
   uint64_t* kb_empty = bars + 29;  // [2] ... and consumed by the 8 softmax warps
   uint64_t* g_empty = bars + 31;   // [2] gate / output tile drained by the TMA stores of the 4 row quarters
@@ -133,21 +133,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nkv = (p.n + 127) / 128;
   const int nqb = nkv;
   const int total_items = nqb * p.heads * p.nbatch;
-  // Work split.  With two query blocks (n <= 256) CTAs 2c and 2c+1 walk the SAME contiguous range of (h, b') units, one per
-  // query block: they load the same K/V tiles at about the same time, so the second read hits L2 instead of HBM, and each
-  // keeps the bias tiles of its own (h, query block) resident.  Otherwise item id = ((h * nqb + qb) * nbatch + b') and this
-  // CTA owns the ids [item0, item0 + my_items).
-  const bool paired = (nqb == 2) && (gridDim.x % 2 == 0);
+  // Work split.  With 2..8 query blocks the CTAs form groups of nqb: the CTAs of a group walk the SAME contiguous range of
+  // (h, b') units, one per query block, so they load the same K/V tiles at about the same time and all but the first read
+  // hit L2 instead of HBM (measured at n = 384 / 512 with one item per CTA and (h, qb, b') order: 1.2-2.0 GB of DRAM reads per
+  // launch for 0.6 GB of operands, the kernel was DRAM bound); for n <= 256 each CTA also keeps the bias tiles of its
+  // (h, query block) resident.  Otherwise item id = ((h * nqb + qb) * nbatch + b') and this CTA owns the ids
+  // [item0, item0 + my_items).
+  const bool paired = (nqb >= 2) && (nqb <= 8) && (gridDim.x % nqb == 0);
   const int n_units = paired ? p.heads * p.nbatch : total_items;
-  const int n_owners = paired ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
-  const int owner = paired ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
+  const int n_owners = paired ? static_cast<int>(gridDim.x) / nqb : static_cast<int>(gridDim.x);
+  const int owner = paired ? static_cast<int>(blockIdx.x) / nqb : static_cast<int>(blockIdx.x);
   const int item0 = static_cast<int>(static_cast<long long>(n_units) * owner / n_owners);
   const int my_items = static_cast<int>(static_cast<long long>(n_units) * (owner + 1) / n_owners) - item0;
   auto decode = [&](int it, int& qb_, int& h_, int& b_) {
     const int id = item0 + it;
     b_ = id % p.nbatch;
     if (paired) {
-      qb_ = static_cast<int>(blockIdx.x) & 1;
+      qb_ = static_cast<int>(blockIdx.x) % nqb;
       h_ = id / p.nbatch;
     } else {
       qb_ = (id / p.nbatch) % nqb;
@@ -187,7 +189,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     mbar_init(&p_full[0], ATTN_SM_WARPS);
     mbar_init(&p_full[1], ATTN_SM_WARPS);
-    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -349,7 +350,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_bf16_ts(tmem_base + O_COL + (it & 1) * 64, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (j != 0 || k != 0) ? 1u : 0u);
         }
         umma_commit(&v_empty[g % nst]);
-        umma_commit(pv_done);
         if (j == nkv - 1) umma_commit(&o_full[it & 1]);
       }
       __syncwarp();
@@ -536,9 +536,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l_run = l_run * corr + (ls0 + ls1);
       m_run = m_new;
 
-      // the previous P V must have retired before O is rescaled (rare: the running maximum moved by more than 2^8)
+      // the previous P V must have retired before O is rescaled (rare: the running maximum moved by more than 2^8).  Its
+      // retirement is the event that frees its V stage, so v_empty of block g - 1 is the barrier to watch: that barrier
+      // cannot complete another phase before this thread has written P(g) (the next P V on the stage needs it).
       if (j > 0 && rescale) {
-        mbar_wait(pv_done, (g - 1) & 1);
+        mbar_wait(&v_empty[(g - 1) % nst], (((g - 1) / nst) & 1));
         tc_fence_after();
         if (o_owner) {
           uint32_t o[16];

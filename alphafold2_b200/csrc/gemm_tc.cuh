@@ -59,6 +59,11 @@ struct GemmParams {
   // plane pairs (A, B) = (hi, lo), (lo, hi), (hi, hi): C = A_hi B_lo + A_lo B_hi + A_hi B_hi in the fp32 accumulator, i.e.
   // ~16 mantissa bits per operand (the dropped lo x lo term is 2^-18 relative).  nseg = 1: plain bf16 operands, rank-3 maps.
   int nseg;
+  // Operands gathered from several ranks ("pieces", alphafold2_b200/parallel.py): an all-gather concatenates the per-rank
+  // shards [c][rows_p][k] along the outermost axis, so rows r = p * pr + rr of one channel are pr-row pieces piece_stride
+  // apart.  Rank-4 maps (k | mn, row | k, piece, batch) address them in place -- one launch instead of one per piece.
+  //   a_pr / b_pr: rows (K-major) or columns (MN-major) per piece of A / B; 0 = plain rank-3 map.
+  int a_pr, b_pr;
   NTile tile;
 };
 
@@ -244,8 +249,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_4d(sb + h * 8192, &tmB, &full_bar[stage], nt * BN + h * 64, kb * GEMM_BK, hb, b);
             }
           } else if constexpr (!MN_MAJOR) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM, b);
-            tma_load_3d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN, b);
+            if (p.a_pr > 0) tma_load_4d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, (mt * GEMM_BM) % p.a_pr, (mt * GEMM_BM) / p.a_pr, b);
+            else tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM, b);
+            if (p.b_pr > 0) tma_load_4d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, (nt * BN) % p.b_pr, (nt * BN) / p.b_pr, b);
+            else tma_load_3d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN, b);
+          } else if (p.a_pr > 0 || p.b_pr > 0) {
+#pragma unroll
+            for (int h = 0; h < GEMM_BM / 64; ++h) {
+              const int m = mt * GEMM_BM + h * 64;
+              if (p.a_pr > 0) tma_load_4d(sa + h * 8192, &tmA, &full_bar[stage], m % p.a_pr, kb * GEMM_BK, m / p.a_pr, b);
+              else tma_load_3d(sa + h * 8192, &tmA, &full_bar[stage], m, kb * GEMM_BK, b);
+            }
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h) {
+              const int n = nt * BN + h * 64;
+              if (p.b_pr > 0) tma_load_4d(sb + h * 8192, &tmB, &full_bar[stage], n % p.b_pr, kb * GEMM_BK, n / p.b_pr, b);
+              else tma_load_3d(sb + h * 8192, &tmB, &full_bar[stage], n, kb * GEMM_BK, b);
+            }
           } else {
             // operand stored [k][mn]: 64-wide mn boxes, each 64 k-rows x 128 B = 8 KB
 #pragma unroll

@@ -20,6 +20,7 @@ int g_proj_ctas = 2;
 int g_proj_wide = 1;              // 1: 64-column epilogue steps where the segment width allows (AF2_PROJ_WIDE)
 int g_proj_balance = 1;           // 1: equal (row unit, column tile) ranges per cluster; 0: round-robin items (AF2_PROJ_BALANCE)
 long long* g_proj_trace = nullptr; // device buffer of 1024 stamps when AF2_PROJ_TRACE=1 (debug only)
+int g_proj_l2pf = 1;              // 1: producer warps prefetch the next item's rows into L2 (AF2_PROJ_L2PF)
 double g_proj_prod_tiles = 4.0;   // cost of producing one A tile in units of one 256-column MMA tile (AF2_PROJ_PRODTILES)
 
 // can this LN -> Linear cluster run on the fused kernel?
@@ -67,6 +68,7 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   p.nsplit = best;
   p.balance = g_proj_balance;
   p.trace = g_proj_trace;
+  p.l2_prefetch = g_proj_l2pf;
   const long long items = p.balance ? (long long)m_units * p.n_tiles_total : (long long)m_units * p.nsplit;
   const int clusters = (int)(items < max_clusters ? items : max_clusters);
   ProfScope ps(s, KC_GEMM_LINEAR, flops, bytes);

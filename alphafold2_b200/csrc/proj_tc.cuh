@@ -70,6 +70,7 @@ struct ProjParams {
   int balance;                   // 1: every cluster owns a contiguous range of the flat (row unit, column tile) sequence
   long long* trace;              // debug (AF2_PROJ_TRACE=1): clock64 stamps of cluster 0's leader CTA, see tools/proj_trace.py
   int m_tiles;                   // ceil(T / 128)
+  int l2_prefetch;               // 1: producers prefetch the next item's rows into L2 (AF2_PROJ_L2PF)
 };
 
 template <int CTAS>
@@ -102,8 +103,12 @@ template <int EK>
 __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t* g, float rs, uint32_t (&pk)[16]) {
   constexpr int mode = EpiTraits<EK>::mode, act = EpiTraits<EK>::act;
   const f32x2 rs2 = pack2(rs, rs);
+#ifndef AF2_RCP_SHARE
+#define AF2_RCP_SHARE 1
+#endif
+#if !AF2_RCP_SHARE
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < 16; ++j) {      // A/B reference: one MUFU.RCP per element (round-1 epilogue)
     f32x2 a = pack2(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
     if constexpr (mode == EPI_GATED_BF16) {
       const f32x2 gg = pack2(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
@@ -116,6 +121,39 @@ __device__ __forceinline__ void proj_finish32(const uint32_t* u, const uint32_t*
     float lo, hi;
     unpack2(a, lo, hi);
     pk[j] = pack_bf16x2(lo, hi);
+  }
+  return;
+#endif
+  // four columns per step: the sigmoid / GELU forms share one MUFU reciprocal between four values (common.cuh)
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    f32x2 a = pack2(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
+    f32x2 b = pack2(__uint_as_float(u[2 * j + 2]), __uint_as_float(u[2 * j + 3]));
+    if constexpr (mode == EPI_GATED_BF16) {
+      const f32x2 ga = pack2(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
+      const f32x2 gb = pack2(__uint_as_float(g[2 * j + 2]), __uint_as_float(g[2 * j + 3]));
+      f32x2 fa, fb;
+      if constexpr (act == ACT_GELU) gelu_fast4(ga, gb, fa, fb);
+      else sigmoidf_fast4(ga, gb, fa, fb);
+      a = mul2(a, fa);
+      b = mul2(b, fb);
+    } else {
+      if constexpr (act == ACT_SIGMOID) {
+        f32x2 fa, fb;
+        sigmoidf_fast4(a, b, fa, fb);
+        a = fa;
+        b = fb;
+      }
+    }
+    if constexpr (EpiTraits<EK>::rowscale) {
+      a = mul2(a, rs2);
+      b = mul2(b, rs2);
+    }
+    float lo, hi;
+    unpack2(a, lo, hi);
+    pk[j] = pack_bf16x2(lo, hi);
+    unpack2(b, lo, hi);
+    pk[j + 1] = pack_bf16x2(lo, hi);
   }
 }
 
@@ -336,7 +374,7 @@ __device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abu
 template <int NJ, int NP, class ItemRow, class WaitEmpty, class SignalFull>
 __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, int d, float inv_d, float eps, uint8_t* a_base,
                                                    int my_items, int pi, int lane, ItemRow item_row0, WaitEmpty wait_empty,
-                                                   SignalFull signal_full) {
+                                                   SignalFull signal_full, bool l2_prefetch) {
   const int sub = lane & 7, rg = lane >> 3;
   constexpr int STEPS = 32;                       // 128 rows / 4
   auto row_ptr = [&](long long row) { return reinterpret_cast<const float4*>(x + row * d) + sub; };
@@ -350,7 +388,7 @@ __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, 
     uint8_t* abuf = a_base + (it & 1) * PROJ_A_BUF;
     wait_empty(it);
     const long long m_next = (it + 1 < my_items) ? item_row0(it + 1) : -1;
-    if (m_next >= 0) {
+    if (m_next >= 0 && l2_prefetch) {
       // pull the next item's tile (128 rows) into L2: one 128-byte line per lane and round, shared by the NP producer warps
       const char* nb = reinterpret_cast<const char*>(x + m_next * d);
       const long long nrows = (m_next + 128 <= T) ? 128 : (T > m_next ? T - m_next : 0);
@@ -652,9 +690,9 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     };
     uint8_t* a_base = smem + L::A_OFF;
     const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32)
-    if (nj == 8) proj_producer_loop<8, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
-    else if (nj == 4) proj_producer_loop<4, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
-    else proj_producer_loop<6, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full);
+    if (nj == 8) proj_producer_loop<8, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
+    else if (nj == 4) proj_producer_loop<4, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
+    else proj_producer_loop<6, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
   }
 
   __syncwarp();

@@ -114,14 +114,22 @@ def randomize_zero_init_(model, std=0.02, seed=1234):
 # CPU arm: oracle port of the reference (the Python reference itself cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------------------------
 def host_threads():
-    """All the host threads the CPU arm can use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the count is set
-    explicitly (SURVEY.md 8d / BASELINE.md 3.3: torch.set_num_threads(os.cpu_count()))."""
-    n = os.cpu_count() or 1
+    """All the host CORES the CPU arm can use.  torchrun exports OMP_NUM_THREADS=1 to its workers (round 1's N>1 CPU arm ran
+    on one thread), so the count is set explicitly -- to the PHYSICAL cores: with one thread per hyper-thread (128 on the
+    pool's 64-core hosts) MKL / OpenMP oversubscribe and the block takes 131 s instead of 6.9 s (measured, profiles/r02a)."""
+    n = None
     try:
-        n = len(os.sched_getaffinity(0)) or n
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        n = None
+    if not n:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    torch.set_num_threads(n)
+    torch.set_num_threads(int(n))
     return torch.get_num_threads()
 
 

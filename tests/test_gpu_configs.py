@@ -9,7 +9,7 @@ MSA rows fully masked."""
 import pytest
 import torch
 
-from gpu_util import autocast_yardstick, check, dev
+from gpu_util import autocast_yardstick, check, depth_gates, dev
 from oracle import evoformer_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -65,7 +65,7 @@ def test_c2_alphafold2_forward_depth12():
         ref = O.alphafold2_distogram(dev(st, torch.float64), *args, dtype=torch.float64, chunk=64)
         ac = autocast_yardstick(lambda: O.alphafold2_distogram(dev(st), *args, chunk=64))
     assert tuple(ret.distance.shape) == (1, N, N, 37)
-    check("C2/alphafold2_forward/depth12/distance", ret.distance, ref, ac.float())
+    check("C2/alphafold2_forward/depth12/distance", ret.distance, ref, ac.float(), **depth_gates(12))
 
 
 def test_c2_evoformer_depth12():
@@ -81,8 +81,8 @@ def test_c2_evoformer_depth12():
     with torch.no_grad():
         rx, rm = O.evoformer(dev(w, torch.float64), "", x.double().cuda(), m.double().cuda(), 8, 12, mask.cuda(), msa_mask.cuda(), chunk=64)
         ax, am = autocast_yardstick(lambda: O.evoformer(dev(w), "", x.cuda(), m.cuda(), 8, 12, mask.cuda(), msa_mask.cuda(), chunk=64))
-    check("C2/evoformer/depth12/x", xo, rx, ax.float())
-    check("C2/evoformer/depth12/m", mo, rm, am.float())
+    check("C2/evoformer/depth12/x", xo, rx, ax.float(), **depth_gates(12))
+    check("C2/evoformer/depth12/m", mo, rm, am.float(), **depth_gates(12))
 
 
 @pytest.mark.parametrize("tag,N,S", [("C3", 384, 512), ("C4", 512, 1024)])

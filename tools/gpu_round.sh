@@ -8,13 +8,13 @@ mkdir -p gpurun_out
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 if has tests; then
   rm -f gpurun_out/parity_report.jsonl
-  timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider -x 2>&1 | tail -25 > gpurun_out/test_gpu_${TAG}.log
-  echo "tests rc=${PIPESTATUS[0]}"; tail -6 gpurun_out/test_gpu_${TAG}.log
+  timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/test_gpu_${TAG}.log
+  echo "tests rc=${PIPESTATUS[0]}"; grep -E 'FAILED|ERROR|passed|failed' gpurun_out/test_gpu_${TAG}.log | tail -30
   cp gpurun_out/parity_report.jsonl gpurun_out/parity_report_${TAG}.jsonl 2>/dev/null
 fi
 if has bench; then
   timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_${TAG}.err
-  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; echo "bench ref rc=$?"
+  timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; echo "bench ref rc=$?"
   python - <<PY
 import json
 try:

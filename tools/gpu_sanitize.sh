@@ -7,7 +7,7 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 SAN=${SAN:-/usr/local/cuda/bin/compute-sanitizer}
 for tool in memcheck racecheck synccheck; do
-  AF2_SAN_CASE=all timeout 900 $SAN --tool $tool --print-limit 20 --error-exitcode 9 \
+  AF2_SAN_CASE=all timeout ${SAN_TIMEOUT:-300} $SAN --tool $tool --print-limit 20 --error-exitcode 9 \
       python tools/sanitize_cases.py > gpurun_out/sanitize_${tool}_${TAG}.log 2>&1
   rc=$?
   echo "sanitize $tool rc=$rc : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|SYNCCHECK SUMMARY' gpurun_out/sanitize_${tool}_${TAG}.log | tail -1)"

@@ -35,7 +35,7 @@ def kernel_class(name):
 
 
 def to_bytes(v, unit):
-    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     return float(v) * m.get(unit, 1)
 
 
@@ -47,14 +47,18 @@ def main(path, out_csv, out_json=None):
     traffic = {}
     with open(out_csv, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["launch"] + [f"{n}[{u}]" if u else n for _, n, u in cols])
+        w.writerow(["launch"] + [(f"{n}[Mbyte]" if n.startswith("dram_") and n.endswith("_MB") else (f"{n}[us]" if n == "time_us" else (f"{n}[{u}]" if u else n))) for _, n, u in cols])
         for i, r in enumerate(rows[2:]):
             out = [i]
             name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
-            for c, n, _ in cols:
+            for c, n, u in cols:
                 v = r[c]
                 if n == "kernel":
                     v = name
+                elif n.startswith("dram_") and n.endswith("_MB"):
+                    v = f"{to_bytes(v, u) / 1e6:.3f}"          # ncu picks one unit per column and capture: normalise to MB
+                elif n == "time_us":
+                    v = f"{float(v) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(u, 1.0):.3f}"
                 else:
                     try:
                         v = f"{float(v):.3f}".rstrip("0").rstrip(".")
