@@ -398,8 +398,9 @@ class Evoformer(nn.Module):
             xo, mo = _f32c(x), _f32c(m)
             mk = mask.bool().contiguous() if exists(mask) else None
             mmk = msa_mask.bool().contiguous() if exists(msa_mask) else None
-            for layer in self.layers:
-                layer.update_(xo, mo, mk, mmk)
+            with ops.l2_resident(xo):
+                for layer in self.layers:
+                    layer.update_(xo, mo, mk, mmk)
         return xo.to(x.dtype), mo.to(m.dtype)
 
     def run_(self, x, m, mask=None, msa_mask=None):
@@ -410,8 +411,9 @@ class Evoformer(nn.Module):
         with torch.no_grad():
             mk = mask.bool().contiguous() if exists(mask) else None
             mmk = msa_mask.bool().contiguous() if exists(msa_mask) else None
-            for layer in self.layers:
-                layer.update_(x, m, mk, mmk)
+            with ops.l2_resident(x):
+                for layer in self.layers:
+                    layer.update_(x, m, mk, mmk)
         return x, m
 
 

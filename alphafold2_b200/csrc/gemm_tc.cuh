@@ -54,16 +54,19 @@ struct GemmParams {
   long long ld_resid;
   long long out_batch_stride;  // elements
   int cm_inner, cm_pitch;      // channel-major: row r -> (r / cm_inner) * cm_pitch + r % cm_inner
-  // Split-bf16 ("bf16x3", strict precision) operands: every fp32 operand value v is stored as two bf16 planes hi = bf16(v),
-  // lo = bf16(v - hi) (tensor maps of rank 4: k, row, plane, batch) and the k loop runs nseg = 3 passes over K with the
-  // plane pairs (A, B) = (hi, lo), (lo, hi), (hi, hi): C = A_hi B_lo + A_lo B_hi + A_hi B_hi in the fp32 accumulator, i.e.
-  // ~16 mantissa bits per operand (the dropped lo x lo term is 2^-18 relative).  nseg = 1: plain bf16 operands, rank-3 maps.
+  // Split-bf16 (strict precision) operands: every fp32 operand value v is stored as bf16 planes p0 = bf16(v),
+  // p1 = bf16(v - p0) [, p2 = bf16(v - p0 - p1)] (tensor maps of rank 4: k, row, plane, batch) and the k loop makes nseg passes
+  // over K, one per plane pair (A plane, B plane), smallest products first, all into the same fp32 accumulator:
+  //   nseg = 3 (two planes,   ~16 mantissa bits): (0,1) (1,0) (0,0)
+  //   nseg = 6 (three planes,  24 mantissa bits): (0,2) (2,0) (1,1) (0,1) (1,0) (0,0)      <- strict mode
+  // nseg = 1: plain bf16 operands, rank-3 maps.
   int nseg;
   // Operands gathered from several ranks ("pieces", alphafold2_b200/parallel.py): an all-gather concatenates the per-rank
   // shards [c][rows_p][k] along the outermost axis, so rows r = p * pr + rr of one channel are pr-row pieces piece_stride
   // apart.  Rank-4 maps (k | mn, row | k, piece, batch) address them in place -- one launch instead of one per piece.
   //   a_pr / b_pr: rows (K-major) or columns (MN-major) per piece of A / B; 0 = plain rank-3 map.
   int a_pr, b_pr;
+  int x_evict_last;            // 1: residual loads / output stores of the fp32 stream carry an L2 evict_last hint (EK_RESID_F32_W)
   NTile tile;
 };
 
@@ -235,8 +238,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if (nseg > 1) {
-            // split operands (rank-4 maps): small cross terms first, hi x hi last
-            const int ha = (seg == 1) ? 1 : 0, hb = (seg == 0) ? 1 : 0;
+            // split operands (rank-4 maps): plane pair of this pass, small cross terms first, p0 x p0 last
+            int ha, hb;
+            if (nseg == 3) { ha = (seg == 1) ? 1 : 0; hb = (seg == 0) ? 1 : 0; }
+            else { ha = (0x021010 >> (4 * (5 - seg))) & 0xf; hb = (0x201100 >> (4 * (5 - seg))) & 0xf; }
             if constexpr (!MN_MAJOR) {
               tma_load_4d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM, ha, b);
               tma_load_4d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN, hb, b);
@@ -352,6 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* rbar = wres_bar + (warp - 4) * 2;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const NTile tl = p.tile;
+    const uint64_t xpol = l2_policy(p.x_evict_last != 0);
     const int my_tiles = (total_tiles > static_cast<int>(blockIdx.x)) ? (total_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
     constexpr int CPW = 4;                                   // chunks per warp and tile (256 columns / 32 / 2 warps)
     const int total_chunks = my_tiles * CPW;
@@ -366,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       chunk_coords(k, m0w, colc);
       tma_store_wait_read<0>();                              // the store that used this buffer (chunk k - 2) has read it
       mbar_arrive_expect_tx(&rbar[k & 1], 4096);
-      tma_load_3d(wbuf + (k & 1) * 4096, &tmR, &rbar[k & 1], colc, m0w, 0);
+      tma_load_3d_hint(wbuf + (k & 1) * 4096, &tmR, &rbar[k & 1], colc, m0w, 0, xpol);
     };
     if (lane == 0 && total_chunks > 0) prefetch(0);
     for (int k = 0; k < total_chunks; ++k) {
@@ -403,7 +409,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tmC, eb, colc, m0w, 0);
+        tma_store_3d_hint(&tmC, eb, colc, m0w, 0, xpol);
         tma_store_commit();
       }
     }

@@ -69,6 +69,7 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   p.balance = g_proj_balance;
   p.trace = g_proj_trace;
   p.l2_prefetch = g_proj_l2pf;
+  p.x_evict_last = x_hint(p.T, p.d);
   const long long items = p.balance ? (long long)m_units * p.n_tiles_total : (long long)m_units * p.nsplit;
   const int clusters = (int)(items < max_clusters ? items : max_clusters);
   ProfScope ps(s, KC_GEMM_LINEAR, flops, bytes);

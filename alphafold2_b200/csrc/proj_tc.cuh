@@ -71,6 +71,7 @@ struct ProjParams {
   long long* trace;              // debug (AF2_PROJ_TRACE=1): clock64 stamps of cluster 0's leader CTA, see tools/proj_trace.py
   int m_tiles;                   // ceil(T / 128)
   int l2_prefetch;               // 1: producers prefetch the next item's rows into L2 (AF2_PROJ_L2PF)
+  int x_evict_last;              // 1: loads of x carry an L2 evict_last hint (AF2_X_EVICT_LAST)
 };
 
 template <int CTAS>
@@ -311,9 +312,9 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 }
 
 template <int NJ>
-__device__ __forceinline__ void proj_load_quad(RowQuad& b, const float4* xr, bool live) {
+__device__ __forceinline__ void proj_load_quad(RowQuad& b, const float4* xr, bool live, uint64_t pol) {
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) b.v[j] = live ? ldg_stream(xr + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NJ; ++j) b.v[j] = live ? ldg_stream_hint(xr + j * 8, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <int NJ>
@@ -374,14 +375,15 @@ __device__ __forceinline__ void proj_process_quad(const RowQuad& b, uint8_t* abu
 template <int NJ, int NP, class ItemRow, class WaitEmpty, class SignalFull>
 __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, int d, float inv_d, float eps, uint8_t* a_base,
                                                    int my_items, int pi, int lane, ItemRow item_row0, WaitEmpty wait_empty,
-                                                   SignalFull signal_full, bool l2_prefetch) {
+                                                   SignalFull signal_full, bool l2_prefetch, bool x_evict_last) {
   const int sub = lane & 7, rg = lane >> 3;
+  const uint64_t pol = l2_policy(x_evict_last);
   constexpr int STEPS = 32;                       // 128 rows / 4
   auto row_ptr = [&](long long row) { return reinterpret_cast<const float4*>(x + row * d) + sub; };
   RowQuad qa, qb;
   if (my_items > 0) {
     const long long row = item_row0(0) + pi * 4 + rg;
-    proj_load_quad<NJ>(qa, row_ptr(row), row < T);
+    proj_load_quad<NJ>(qa, row_ptr(row), row < T, pol);
   }
   for (int it = 0; it < my_items; ++it) {
     const long long m0 = item_row0(it);
@@ -394,7 +396,8 @@ __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, 
       const long long nrows = (m_next + 128 <= T) ? 128 : (T > m_next ? T - m_next : 0);
       const long long nbytes = nrows * d * 4;
       for (long long o = (pi * 32 + lane) * 128LL; o < nbytes; o += NP * 32 * 128LL)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+        if (x_evict_last) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nb + o));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
     }
     // steps pi, pi + NP, ...: process qa while qb's loads are in flight and vice versa
     int st = pi;
@@ -406,7 +409,7 @@ __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, 
         if (st1 < STEPS) row = m0 + st1 * 4 + rg;
         else if (m_next >= 0) row = m_next + pi * 4 + rg;           // first step of the next item
         else { row = 0; any = false; }
-        proj_load_quad<NJ>(qb, row_ptr(row), any && row < T);
+        proj_load_quad<NJ>(qb, row_ptr(row), any && row < T, pol);
       }
       proj_process_quad<NJ>(qa, abuf, st * 4 + rg, (m0 + st * 4 + rg) < T, inv_d, eps, sub);
       if (st1 >= STEPS) { qa = qb; break; }
@@ -415,7 +418,7 @@ __device__ __forceinline__ void proj_producer_loop(const float* x, long long T, 
         if (st2 < STEPS) row = m0 + st2 * 4 + rg;
         else if (m_next >= 0) row = m_next + pi * 4 + rg;
         else { row = 0; any = false; }
-        proj_load_quad<NJ>(qa, row_ptr(row), any && row < T);
+        proj_load_quad<NJ>(qa, row_ptr(row), any && row < T, pol);
       }
       proj_process_quad<NJ>(qb, abuf, st1 * 4 + rg, (m0 + st1 * 4 + rg) < T, inv_d, eps, sub);
       st = st2;
@@ -690,9 +693,9 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     };
     uint8_t* a_base = smem + L::A_OFF;
     const int nj = p.d >> 5;                     // float4 chunks per lane (d / 32)
-    if (nj == 8) proj_producer_loop<8, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
-    else if (nj == 4) proj_producer_loop<4, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
-    else proj_producer_loop<6, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0);
+    if (nj == 8) proj_producer_loop<8, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0, p.x_evict_last != 0);
+    else if (nj == 4) proj_producer_loop<4, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0, p.x_evict_last != 0);
+    else proj_producer_loop<6, PROJ_NPROD>(p.x, p.T, p.d, p.inv_d, p.eps, a_base, my_items, pi, lane, item_row0, wait_empty, signal_full, p.l2_prefetch != 0, p.x_evict_last != 0);
   }
 
   __syncwarp();

@@ -12,21 +12,21 @@ GemmCall split_call(const void* A, long long lda, long long a_half, long long a_
   memset(&c, 0, sizeof(c));
   c.A = A; c.lda = lda; c.a_half = a_half; c.a_batch = a_batch;
   c.Bm = Bm; c.ldb = ldb; c.b_half = b_half; c.b_batch = b_batch;
-  c.M = M; c.N = N; c.K = K; c.batch = batch; c.mn_major = mn_major; c.bn = pick_bn(N); c.nseg = 3;
+  c.M = M; c.N = N; c.K = K; c.batch = batch; c.mn_major = mn_major; c.bn = pick_bn(N); c.nseg = SPL_NSEG;
   return c;
 }
 
 // out[T][N] fp32 = A_split[T][2][Pk] x W_split[N][2][Pk]^T + bias
 int strict_linear_f32(const __nv_bfloat16* A, const void* W, const float* bias, float* out, long long T, int N, int K, cudaStream_t s) {
   const int Pk = a8(K);
-  GemmCall c = split_call(A, 2LL * Pk, Pk, 0, W, 2LL * Pk, Pk, 0, (int)T, N, K, 1, false);
+  GemmCall c = split_call(A, (long long)SPL * Pk, Pk, 0, W, (long long)SPL * Pk, Pk, 0, (int)T, N, K, 1, false);
   c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = out; c.ld_out = N; c.bias = bias;
   return launch_gemm(c, s);
 }
 // x[T][N] fp32 += A_split[T][2][Pk] x W_split[N][2][Pk]^T + bias   (output projections with residual)
 int strict_linear_resid(const __nv_bfloat16* A, const void* W, const float* bias, float* x, long long T, int N, int K, cudaStream_t s) {
   const int Pk = a8(K);
-  GemmCall c = split_call(A, 2LL * Pk, Pk, 0, W, 2LL * Pk, Pk, 0, (int)T, N, K, 1, false);
+  GemmCall c = split_call(A, (long long)SPL * Pk, Pk, 0, W, (long long)SPL * Pk, Pk, 0, (int)T, N, K, 1, false);
   c.mode = EPI_RESID_F32; c.out = x; c.ld_out = N; c.bias = bias; c.resid = x; c.ld_resid = N;
   return launch_gemm(c, s);
 }
@@ -69,22 +69,22 @@ int strict_tok2chan(const float* src, long long ld, int val_off, int gate_off, c
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------ utilities (tests)
-// y split [rows][2][align8(K)] of x fp32 [rows][K]
+// y split [rows][SPL][align8(K)] of x fp32 [rows][K]
 int af2_split_bf16(const float* x, void* y, long long rows, int K, af2_stream_t stream) {
   return strict_ln_split(x, nullptr, nullptr, static_cast<__nv_bfloat16*>(y), rows, K, static_cast<cudaStream_t>(stream));
 }
 
-// C[b][m][n] fp32 = sum_k A[b][m][k] B[b][n][k] on split operands A [batch][M][2][P], B [batch][N][2][P], P = align8(K)
+// C[b][m][n] fp32 = sum_k A[b][m][k] B[b][n][k] on split operands A [batch][M][SPL][P], B [batch][N][SPL][P], P = align8(K)
 int af2_gemm_split_f32(const void* A, const void* Bm, float* C, long long ldc, int M, int N, int K, int batch, af2_stream_t stream) {
   const int P = a8(K);
-  GemmCall c = split_call(A, 2LL * P, P, (long long)M * 2 * P, Bm, 2LL * P, P, (long long)N * 2 * P, M, N, K, batch, false);
+  GemmCall c = split_call(A, (long long)SPL * P, P, (long long)M * SPL * P, Bm, (long long)SPL * P, P, (long long)N * SPL * P, M, N, K, batch, false);
   c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = C; c.ld_out = ldc; c.out_batch = (long long)M * ldc;
   return launch_gemm(c, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ FeedForward
 long long af2_feed_forward_strict_workspace(long long tokens, int d, int hidden) {
-  return align_up(tokens * 2 * a8(d) * 2, 256) + align_up(tokens * 2 * hidden * 4, 256) + align_up(tokens * 2 * a8(hidden) * 2, 256) + 1024;
+  return align_up(tokens * SPL * a8(d) * 2, 256) + align_up(tokens * 2 * hidden * 4, 256) + align_up(tokens * SPL * a8(hidden) * 2, 256) + 1024;
 }
 
 int af2_feed_forward_strict(const af2_ff_weights_strict* w, float* x, long long tokens, int d, int hidden, void* workspace,
@@ -95,9 +95,9 @@ int af2_feed_forward_strict(const af2_ff_weights_strict* w, float* x, long long 
   if (d % 4 || hidden % 4) return fail(AF2_ERR_BAD_ARG, "feed_forward_strict: d=%d and hidden=%d must be multiples of 4", d, hidden);
   if (tokens > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "feed_forward_strict: too many tokens");
   Arena ar(workspace, workspace_bytes);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(tokens * 2 * a8(d));
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(tokens * SPL * a8(d));
   float* h = ar.take<float>(tokens * 2 * hidden);
-  __nv_bfloat16* hs = ar.take<__nv_bfloat16>(tokens * 2 * a8(hidden));
+  __nv_bfloat16* hs = ar.take<__nv_bfloat16>(tokens * SPL * a8(hidden));
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "feed_forward_strict: workspace too small");
   AF2_TRY(strict_ln_split(x, w->ln_gamma, w->ln_beta, xs, tokens, d, s));
   AF2_TRY(strict_linear_f32(xs, w->w1, w->b1, h, tokens, 2 * hidden, d, s));
@@ -122,10 +122,10 @@ long long af2_axial_attention_strict_workspace(int B, int h, int wdim, int d, in
   const int n = row_attn ? wdim : h, nb = row_attn ? h : wdim;
   const long long ch = strict_attn_chunk(nb, heads, n);
   const int Pd = a8(dim_head), Pn = a8(n);
-  return align_up(T * 2 * a8(d) * 2, 256) + align_up(T * 4 * I * 4, 256) + align_up(T * 2 * a8(I) * 2, 256) +
+  return align_up(T * SPL * a8(d) * 2, 256) + align_up(T * 4 * I * 4, 256) + align_up(T * SPL * a8(I) * 2, 256) +
          align_up((long long)heads * n * n * 4, 256) +
-         2 * align_up(ch * heads * n * 2 * Pd * 2, 256) + align_up(ch * heads * dim_head * 2 * Pn * 2, 256) +
-         align_up(ch * heads * n * align_up(n, 4) * 4, 256) + align_up(ch * heads * n * 2 * Pn * 2, 256) +
+         2 * align_up(ch * heads * n * SPL * Pd * 2, 256) + align_up(ch * heads * dim_head * SPL * Pn * 2, 256) +
+         align_up(ch * heads * n * align_up(n, 4) * 4, 256) + align_up(ch * heads * n * SPL * Pn * 2, 256) +
          align_up(ch * heads * n * (long long)dim_head * 4, 256) + 4096;
 }
 
@@ -144,15 +144,15 @@ int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const
   const long long lds = align_up(n, 4);
   const bool has_bias = edges != nullptr && w->w_edge != nullptr;
   Arena ar(workspace, workspace_bytes);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(T * 2 * a8(d));
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(T * SPL * a8(d));
   float* p1 = ar.take<float>(T * 4 * I);
-  __nv_bfloat16* og = ar.take<__nv_bfloat16>(T * 2 * Pi);
+  __nv_bfloat16* og = ar.take<__nv_bfloat16>(T * SPL * Pi);
   float* bias = ar.take<float>((long long)heads * n * n);
-  __nv_bfloat16* Q = ar.take<__nv_bfloat16>(ch * heads * n * 2 * Pd);
-  __nv_bfloat16* K = ar.take<__nv_bfloat16>(ch * heads * n * 2 * Pd);
-  __nv_bfloat16* Vt = ar.take<__nv_bfloat16>(ch * heads * dim_head * 2 * Pn);
+  __nv_bfloat16* Q = ar.take<__nv_bfloat16>(ch * heads * n * SPL * Pd);
+  __nv_bfloat16* K = ar.take<__nv_bfloat16>(ch * heads * n * SPL * Pd);
+  __nv_bfloat16* Vt = ar.take<__nv_bfloat16>(ch * heads * dim_head * SPL * Pn);
   float* S = ar.take<float>(ch * heads * n * lds);
-  __nv_bfloat16* P = ar.take<__nv_bfloat16>(ch * heads * n * 2 * Pn);
+  __nv_bfloat16* P = ar.take<__nv_bfloat16>(ch * heads * n * SPL * Pn);
   float* O = ar.take<float>(ch * heads * n * (long long)dim_head);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "axial_attention_strict: workspace too small");
 
@@ -182,7 +182,7 @@ int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const
         CUDA_OK(cudaGetLastError());
       }
       {   // logits S = Q K^T per (b', head)
-        GemmCall c = split_call(Q, 2LL * Pd, Pd, (long long)n * 2 * Pd, K, 2LL * Pd, Pd, (long long)n * 2 * Pd, n, n, dim_head, bh, false);
+        GemmCall c = split_call(Q, (long long)SPL * Pd, Pd, (long long)n * SPL * Pd, K, (long long)SPL * Pd, Pd, (long long)n * SPL * Pd, n, n, dim_head, bh, false);
         c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = S; c.ld_out = lds; c.out_batch = (long long)n * lds;
         AF2_TRY(launch_gemm(c, s));
       }
@@ -194,13 +194,13 @@ int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const
         CUDA_OK(cudaGetLastError());
       }
       {   // O = P V per (b', head): A = P [n][keys], B = V^T [dh][keys]
-        GemmCall c = split_call(P, 2LL * Pn, Pn, (long long)n * 2 * Pn, Vt, 2LL * Pn, Pn, (long long)dim_head * 2 * Pn, n, dim_head, n, bh, false);
+        GemmCall c = split_call(P, (long long)SPL * Pn, Pn, (long long)n * SPL * Pn, Vt, (long long)SPL * Pn, Pn, (long long)dim_head * SPL * Pn, n, dim_head, n, bh, false);
         c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = O; c.ld_out = dim_head; c.out_batch = (long long)n * dim_head;
         AF2_TRY(launch_gemm(c, s));
       }
       {
         ProfScope ps(s, KC_MISC, 0.0, 0.0);
-        strict_gate_split_kernel<<<ew_grid((long long)nbc * n * Pi), 256, 0, s>>>(O, dim_head, p1 + t0 * 4 * I, og + t0 * 2 * Pi, (int)b0, nbc, heads, n, dim_head, Pi, tok_sb, tok_si);
+        strict_gate_split_kernel<<<ew_grid((long long)nbc * n * Pi), 256, 0, s>>>(O, dim_head, p1 + t0 * 4 * I, og + t0 * SPL * Pi, (int)b0, nbc, heads, n, dim_head, Pi, tok_sb, tok_si);
         CUDA_OK(cudaGetLastError());
       }
     }
@@ -212,8 +212,8 @@ int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const
 long long af2_triangle_multiply_strict_workspace(int B, int N, int d) {
   const long long T = (long long)B * N * N;
   const int P8 = a8(N);
-  return align_up(T * 2 * a8(d) * 2, 256) + align_up(T * 5 * d * 4, 256) + 2 * align_up((long long)d * N * 2 * P8 * 2, 256) +
-         align_up((long long)d * N * align_up(N, 4) * 4, 256) + align_up((long long)N * N * 2 * a8(d) * 2, 256) + 2048;
+  return align_up(T * SPL * a8(d) * 2, 256) + align_up(T * 5 * d * 4, 256) + 2 * align_up((long long)d * N * SPL * P8 * 2, 256) +
+         align_up((long long)d * N * align_up(N, 4) * 4, 256) + align_up((long long)N * N * SPL * a8(d) * 2, 256) + 2048;
 }
 
 int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, const unsigned char* mask, int B, int N, int d,
@@ -225,14 +225,14 @@ int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, c
   const long long T = (long long)B * N * N, Tb = (long long)N * N;
   if (T > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "triangle_multiply_strict: too many tokens");
   const int P8 = a8(N), np4 = (int)align_up(N, 4), Pd = a8(d);
-  const long long cs = (long long)N * 2 * P8;        // channel stride of the split operands
+  const long long cs = (long long)N * SPL * P8;      // channel stride of the split operands
   Arena ar(workspace, workspace_bytes);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(T * 2 * Pd);
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>(T * SPL * Pd);
   float* p5 = ar.take<float>(T * 5 * d);             // left | right | left_gate | right_gate | out_gate (pre-activation)
   __nv_bfloat16* Lc = ar.take<__nv_bfloat16>(d * cs);
   __nv_bfloat16* Rc = ar.take<__nv_bfloat16>(d * cs);
   float* Oc = ar.take<float>((long long)d * N * np4);
-  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Tb * 2 * Pd);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Tb * SPL * Pd);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "triangle_multiply_strict: workspace too small");
   AF2_TRY(strict_ln_split(x, w->ln_gamma, w->ln_beta, xs, T, d, s));
   AF2_TRY(strict_linear_f32(xs, w->w5, w->b5, p5, T, 5 * d, d, s));
@@ -245,11 +245,11 @@ int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, c
       CUDA_OK(cudaMemsetAsync(Rc, 0, (size_t)d * cs * 2, s));
     }
     GemmCall c;
-    if (!ingoing) {   // O_c = L_c R_c^T (alphafold2.py:285): K-major operands [c][i][2][P8]
-      AF2_TRY(strict_tok2chan(pb, 5LL * d, 0, 2 * d, mb, Lc, d, N, N, cs, P8, 2LL * P8, s));
-      AF2_TRY(strict_tok2chan(pb, 5LL * d, d, 3 * d, mb, Rc, d, N, N, cs, P8, 2LL * P8, s));
-      c = split_call(Lc, 2LL * P8, P8, cs, Rc, 2LL * P8, P8, cs, N, N, N, d, false);
-    } else {          // O_c[i][j] = sum_k R_c[k][i] L_c[k][j] (alphafold2.py:287, quirk Q6): MN-major operands [c][2][k][P8]
+    if (!ingoing) {   // O_c = L_c R_c^T (alphafold2.py:285): K-major operands [c][i][SPL][P8]
+      AF2_TRY(strict_tok2chan(pb, 5LL * d, 0, 2 * d, mb, Lc, d, N, N, cs, P8, (long long)SPL * P8, s));
+      AF2_TRY(strict_tok2chan(pb, 5LL * d, d, 3 * d, mb, Rc, d, N, N, cs, P8, (long long)SPL * P8, s));
+      c = split_call(Lc, (long long)SPL * P8, P8, cs, Rc, (long long)SPL * P8, P8, cs, N, N, N, d, false);
+    } else {          // O_c[i][j] = sum_k R_c[k][i] L_c[k][j] (alphafold2.py:287, quirk Q6): MN-major operands [c][SPL][k][P8]
       AF2_TRY(strict_tok2chan(pb, 5LL * d, 0, 2 * d, mb, Lc, d, N, N, cs, (long long)N * P8, P8, s));
       AF2_TRY(strict_tok2chan(pb, 5LL * d, d, 3 * d, mb, Rc, d, N, N, cs, (long long)N * P8, P8, s));
       c = split_call(Rc, P8, (long long)N * P8, cs, Lc, P8, (long long)N * P8, cs, N, N, N, d, true);
@@ -270,8 +270,8 @@ int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, c
 long long af2_outer_mean_strict_workspace(int B, int S, int N, int d) {
   const long long Tm = (long long)B * S * N;
   const int P8 = a8(N);
-  return align_up(Tm * 2 * a8(d) * 2, 256) + align_up(Tm * 2 * d * 4, 256) + align_up((long long)2 * d * 2 * S * P8 * 2, 256) +
-         align_up((long long)d * N * align_up(N, 4) * 4, 256) + align_up((long long)N * N * 2 * a8(d) * 2, 256) +
+  return align_up(Tm * SPL * a8(d) * 2, 256) + align_up(Tm * 2 * d * 4, 256) + align_up((long long)2 * d * SPL * S * P8 * 2, 256) +
+         align_up((long long)d * N * align_up(N, 4) * 4, 256) + align_up((long long)N * N * SPL * a8(d) * 2, 256) +
          align_up((long long)N * N * 4, 256) + 2048;
 }
 
@@ -284,13 +284,13 @@ int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const flo
   const long long Tm = (long long)B * S * N, Tmb = (long long)S * N, Txb = (long long)N * N;
   if (Tm > 0x7fffffffLL || (long long)B * Txb > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "outer_mean_strict: too many tokens");
   const int P8 = a8(N), np4 = (int)align_up(N, 4), Pd = a8(d);
-  const long long cs = 2LL * S * P8;                 // channel stride: [c][2][S][P8]
+  const long long cs = (long long)SPL * S * P8;      // channel stride: [c][SPL][S][P8]
   Arena ar(workspace, workspace_bytes);
-  __nv_bfloat16* ms = ar.take<__nv_bfloat16>(Tm * 2 * Pd);
+  __nv_bfloat16* ms = ar.take<__nv_bfloat16>(Tm * SPL * Pd);
   float* p2 = ar.take<float>(Tm * 2 * d);             // left | right
   __nv_bfloat16* LRc = ar.take<__nv_bfloat16>(2LL * d * cs);
   float* Oc = ar.take<float>((long long)d * N * np4);
-  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Txb * 2 * Pd);
+  __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Txb * SPL * Pd);
   float* scale = ar.take<float>(Txb);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_mean_strict: workspace too small");
   AF2_TRY(strict_ln_split(m, w->ln_gamma, w->ln_beta, ms, Tm, d, s));
@@ -393,3 +393,45 @@ int af2_distogram_head(const float* x, const float* gamma, const float* beta, co
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// L2 residency of the fp32 pair stream (experiment knob AF2_L2_PERSIST): an access-policy window on `stream`
+// marks [ptr, ptr + bytes) as persisting in L2 for every kernel launched on it afterwards.  ptr == NULL clears the window.
+// =================================================================================================
+extern "C" int af2_l2_persist(const void* ptr, long long bytes, float hit_ratio, af2_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int dev = cur_dev();
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (!ptr || bytes <= 0) {
+    attr.accessPolicyWindow.base_ptr = nullptr;
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitRatio = 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+    CUDA_OK(cudaCtxResetPersistingL2Cache());
+    return AF2_OK;
+  }
+  int max_persist = 0, max_window = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  if (max_persist <= 0 || max_window <= 0) return fail(AF2_ERR_CUDA, "l2_persist: device reports no persisting L2 (%d / %d)", max_persist, max_window);
+  static long long limit_set[MAX_DEVICES] = {0};
+  const long long want = bytes < (long long)max_persist ? bytes : (long long)max_persist;
+  if (limit_set[dev] < want) {
+    CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want));
+    limit_set[dev] = want;
+  }
+  attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  attr.accessPolicyWindow.num_bytes = (size_t)(bytes < (long long)max_window ? bytes : (long long)max_window);
+  // if the window is larger than the set-aside, only a matching fraction of it can persist without thrashing
+  float hr = hit_ratio > 0.f ? hit_ratio : 1.0f;
+  const float fit = (float)want / (float)attr.accessPolicyWindow.num_bytes;
+  if (hr > fit) hr = fit;
+  attr.accessPolicyWindow.hitRatio = hr;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return AF2_OK;
+}

@@ -1,32 +1,42 @@
 // SIMT kernels of the STRICT precision mode (alphafold2_b200.set_precision(model, "strict")).
 //
 // Strict mode keeps every activation in fp32 between kernels and feeds the tcgen05 GEMM (gemm_tc.cuh, GemmParams::nseg = 3)
-// with SPLIT-bf16 operands: v = hi + lo, hi = bf16(v), lo = bf16(v - hi), products hi*lo + lo*hi + hi*hi accumulated in
-// fp32 -- ~16 mantissa bits per operand, so the block output matches the reference's fp32 path inside the north star's
-// rtol 1e-3 / atol 1e-4 band (the default mode's bf16 operands cannot: SURVEY.md Appendix B).  The kernels here do the
+// with SPLIT-bf16 operands: v = p0 + p1 + p2 with p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1) (24 mantissa bits),
+// and the six products p0*p2 + p2*p0 + p1*p1 + p0*p1 + p1*p0 + p0*p0 accumulated in fp32 (everything below 2^-24 relative is
+// dropped), so the trunk output matches the reference's fp32 path inside the north star's rtol 1e-3 / atol 1e-4 band even
+// after 12 blocks (two planes / three products leave 2^-17 per operand: 99.994 % of the C2 depth-12 elements in band,
+// measured; the default mode's bf16 operands cannot come close: SURVEY.md Appendix B).  The kernels here do the
 // fp32 element-wise work around those GEMMs (LayerNorm, GEGLU, gates, masks, softmax, layout changes) with exact-grade
 // math (erff / expf, fp32 statistics) and write the split planes.  Throughput is secondary in this mode.
 //
-// Split layouts (P = align8(K) so that every plane row is 16-byte aligned for TMA):
-//   token-major   [rows][2][P]                 row stride 2P, plane stride P
-//   channel-major, k contiguous (K-major)      [c][rows][2][P]
-//   channel-major, mn contiguous (MN-major)    [c][2][k][P]
+// Split layouts (SPL = 3 planes, P = align8(K) so that every plane row is 16-byte aligned for TMA):
+//   token-major   [rows][SPL][P]               row stride SPL * P, plane stride P
+//   channel-major, k contiguous (K-major)      [c][rows][SPL][P]
+//   channel-major, mn contiguous (MN-major)    [c][SPL][k][P]
 #pragma once
 #include "common.cuh"
 #include "simt_kernels.cuh"
 
 namespace af2 {
 
-__device__ __forceinline__ void split_store(__nv_bfloat16* hi_p, __nv_bfloat16* lo_p, float v) {
-  const __nv_bfloat16 h = __float2bfloat16(v);
-  *hi_p = h;
-  *lo_p = __float2bfloat16(v - __bfloat162float(h));
+constexpr int SPL = 3;        // bf16 planes per split operand
+constexpr int SPL_NSEG = 6;   // tensor-core passes over K (GemmParams::nseg)
+
+// p[0], p[ps], p[2 ps] <- the three bf16 planes of v (the subtractions are exact in fp32)
+__device__ __forceinline__ void split_store(__nv_bfloat16* p, long long ps, float v) {
+  const __nv_bfloat16 h0 = __float2bfloat16(v);
+  const float r1 = v - __bfloat162float(h0);
+  const __nv_bfloat16 h1 = __float2bfloat16(r1);
+  const float r2 = r1 - __bfloat162float(h1);
+  p[0] = h0;
+  p[ps] = h1;
+  p[2 * ps] = __float2bfloat16(r2);
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_acc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------------------
-// y = LayerNorm(x) * gamma + beta (or y = x when gamma == nullptr) -> split token-major [T][2][P]; one warp per row.
+// y = LayerNorm(x) * gamma + beta (or y = x when gamma == nullptr) -> split token-major [T][SPL][P]; one warp per row.
 // Two-pass statistics in fp32 exactly like nn.LayerNorm (biased variance, eps inside the sqrt).  Pad columns [d, P) zeroed.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) strict_ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -49,17 +59,17 @@ __global__ void __launch_bounds__(256) strict_ln_split_kernel(const float* __res
       }
       rstd = rsqrtf(warp_sum(q) / d + eps);
     }
-    __nv_bfloat16* yr = y + t * 2 * P;
+    __nv_bfloat16* yr = y + t * SPL * P;
     for (int c = lane; c < P; c += 32) {
       float v = 0.f;
       if (c < d) v = gamma ? (xr[c] - mean) * rstd * gamma[c] + beta[c] : xr[c];
-      split_store(yr + c, yr + P + c, v);
+      split_store(yr + c, P, v);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEGLU (alphafold2.py:69-72): h [T][2*hid] = (a | g) fp32 -> a * gelu_erf(g) -> split [T][2][P]
+// GEGLU (alphafold2.py:69-72): h [T][2*hid] = (a | g) fp32 -> a * gelu_erf(g) -> split [T][SPL][P]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) strict_geglu_split_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ y,
                                                                  long long T, int hid, int P) {
@@ -70,14 +80,14 @@ __global__ void __launch_bounds__(256) strict_geglu_split_kernel(const float* __
     const int c = static_cast<int>(idx - t * P);
     float v = 0.f;
     if (c < hid) v = h[t * 2 * hid + c] * gelu_acc(h[t * 2 * hid + hid + c]);
-    split_store(y + t * 2 * P + c, y + t * 2 * P + P + c, v);
+    split_store(y + t * SPL * P + c, P, v);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // attention operands from the fused projection P1 [T][4I] = (q | k | v | gate logits), fp32:
-//   Q, K : split [bh][n][2][Pd]     (q already carries dim_head^-0.5 through the packed weight)
-//   Vt   : split [bh][dh][2][Pn]    (V transposed: row = feature e, column = key j) so that P V is a K-major GEMM
+//   Q, K : split [bh][n][SPL][Pd]     (q already carries dim_head^-0.5 through the packed weight)
+//   Vt   : split [bh][dh][SPL][Pn]    (V transposed: row = feature e, column = key j) so that P V is a K-major GEMM
 // bh = b' * H + h;  token(b', i) = b' * tok_sb + i * tok_si  (row / column fold of AxialAttention, alphafold2.py:228-240)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) strict_qkv_split_kernel(const float* __restrict__ p1, __nv_bfloat16* __restrict__ Q,
@@ -102,9 +112,9 @@ __global__ void __launch_bounds__(256) strict_qkv_split_kernel(const float* __re
       qv = p1[tok * ld + h * dh + e];
       kv = p1[tok * ld + I + h * dh + e];
     }
-    const long long o = (bh * n + i) * 2 * Pd + e;
-    split_store(Q + o, Q + o + Pd, qv);
-    split_store(K + o, K + o + Pd, kv);
+    const long long o = (bh * n + i) * SPL * Pd + e;
+    split_store(Q + o, Pd, qv);
+    split_store(K + o, Pd, kv);
   }
   // v transposed: thread per (bh, e, j in [0, Pn))
   const long long tot_v = static_cast<long long>(nb) * H * dh * Pn;
@@ -118,8 +128,8 @@ __global__ void __launch_bounds__(256) strict_qkv_split_kernel(const float* __re
     const long long bl = bh / H;
     float v = 0.f;
     if (j < n) v = p1[((b0 + bl) * tok_sb + j * tok_si) * ld + 2 * I + h * dh + e];
-    const long long o = (bh * dh + e) * 2 * Pn + j;
-    split_store(Vt + o, Vt + o + Pn, v);
+    const long long o = (bh * dh + e) * SPL * Pn + j;
+    split_store(Vt + o, Pn, v);
   }
 }
 
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(256) strict_pair_bias_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// softmax rows of the logits S [bh][n][lds] (fp32, = q k^T) -> P split [bh][n][2][Pn]; one warp per (bh, i).
+// softmax rows of the logits S [bh][n][lds] (fp32, = q k^T) -> P split [bh][n][SPL][Pn]; one warp per (bh, i).
 //   logits += bias[h][i][j] (fp32 [H][n][n]);  mask semantics of alphafold2.py:162-167 (quirk Q1): where
 //   !(mask[q] & mask[k]) the logit is REPLACED by -FLT_MAX, so a masked query row is uniform over all n keys.
 // ------------------------------------------------------------------------------------------------
@@ -179,17 +189,17 @@ __global__ void __launch_bounds__(256) strict_softmax_split_kernel(const float* 
     for (int j = lane; j < n; j += 32) sum += expf(logit(j) - mx);
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    __nv_bfloat16* pr = P + r * 2 * Pn;
+    __nv_bfloat16* pr = P + r * SPL * Pn;
     for (int j = lane; j < Pn; j += 32) {
       const float v = j < n ? expf(logit(j) - mx) * inv : 0.f;
-      split_store(pr + j, pr + Pn + j, v);
+      split_store(pr + j, Pn, v);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // attention output * sigmoid(gating) (alphafold2.py:184-185): O [bh][n][dh] fp32, gate logits = P1[:, 3I:4I]
-//   -> split token-major [T][2][Pi] rows of the tokens of batch elements [b0, b0 + nb)
+//   -> split token-major [T][SPL][Pi] rows of the tokens of batch elements [b0, b0 + nb)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) strict_gate_split_kernel(const float* __restrict__ O, long long ldo, const float* __restrict__ p1,
                                                                 __nv_bfloat16* __restrict__ og, int b0, int nb, int H, int n, int dh, int Pi,
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(256) strict_gate_split_kernel(const float* __r
       const int h = c / dh, e = c - h * dh;
       v = O[((bl * H + h) * n + i) * ldo + e] * sigmoid_acc(p1[tok * 4LL * I + 3 * I + c]);
     }
-    split_store(og + tok * 2 * Pi + c, og + tok * 2 * Pi + Pi + c, v);
+    split_store(og + tok * SPL * Pi + c, Pi, v);
   }
 }
 
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(256) strict_gate_split_kernel(const float* __r
 // token-major fp32 [T][ld] -> channel-major split operand of a per-channel contraction (32 x 32 smem transpose):
 //   value v(t, c) = src[t][val_off + c] * (gate_off >= 0 ? sigmoid(src[t][gate_off + c]) : 1) * (mask ? mask[t] : 1)
 //   token t = r * inner + k  (r = row of the channel matrix, k = its column);   element (c, r, k, plane) goes to
-//   out[c * cs + plane * hs + r * rs + k]       K-major split:  rs = 2P, hs = P;   MN-major split: rs = P, hs = rows * P
+//   out[c * cs + plane * hs + r * rs + k]       K-major split:  rs = SPL * P, hs = P;   MN-major split: rs = P, hs = rows * P
 // grid = (rows * ceil(inner / 32), ceil(C / 32)), block = 32 x 8
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) strict_tok2chan_split_kernel(const float* __restrict__ src, long long ld, int val_off, int gate_off,
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(256) strict_tok2chan_split_kernel(const float*
     const int c = c0 + cc, k = k0 + tx;
     if (c < C && k < inner) {
       __nv_bfloat16* o = out + static_cast<long long>(c) * cs + static_cast<long long>(r) * rs + k;
-      split_store(o, o + hs, tile[tx][cc]);
+      split_store(o, hs, tile[tx][cc]);
     }
   }
 }
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(256) strict_chan_to_token_kernel(const StrictC
   for (int tk = warp; tk < 32; tk += 8) {
     if (j0 + tk >= p.n) break;
     const long long token = static_cast<long long>(row) * p.n + j0 + tk;
-    __nv_bfloat16* yr = p.y + token * 2 * p.P;
+    __nv_bfloat16* yr = p.y + token * SPL * p.P;
     if (p.mode == 0) {
       float sum = 0.f;
       for (int c = lane; c < p.d; c += 32) sum += tile[c * 33 + tk];
@@ -289,11 +299,11 @@ __global__ void __launch_bounds__(256) strict_chan_to_token_kernel(const StrictC
           const float g = sigmoid_acc(p.gate_src[token * p.gate_ld + p.gate_off + c]);
           o = ((tile[c * 33 + tk] - mean) * rstd * p.gamma[c] + p.beta[c]) * g;
         }
-        split_store(yr + c, yr + p.P + c, o);
+        split_store(yr + c, p.P, o);
       }
     } else {
       const float sc = p.scale ? p.scale[token] : p.scale_const;
-      for (int c = lane; c < p.P; c += 32) split_store(yr + c, yr + p.P + c, c < p.d ? tile[c * 33 + tk] * sc : 0.f);
+      for (int c = lane; c < p.P; c += 32) split_store(yr + c, p.P, c < p.d ? tile[c * 33 + tk] * sc : 0.f);
     }
   }
 }

@@ -35,7 +35,7 @@ def bump_pack_epoch() -> None:
 
 
 def precision_of(module) -> str:
-    """'bf16' (default: bf16 tensor-core operands, fp32 accumulate) or 'strict' (split-bf16 x3 operands, fp32-grade results
+    """'bf16' (default: bf16 tensor-core operands, fp32 accumulate) or 'strict' (split-bf16 operands: 3 planes, 6 tensor-core passes; fp32-grade results
     inside the north star's rtol 1e-3 / atol 1e-4 band).  Set per model with alphafold2_b200.set_precision()."""
     return module.__dict__.get("_af2_precision", _DEFAULT_PRECISION)
 
@@ -260,15 +260,21 @@ def pack_outer_mean(norm_w, norm_b, wl, bl, wr, br, wo, bo) -> Packed:
 # --------------------------------------------------------------------------------------------------
 # strict precision mode: split-bf16 weights (v = hi + lo), fp32 biases / LayerNorm affine
 # --------------------------------------------------------------------------------------------------
+SPLIT_PLANES = 3       # bf16 planes per strict-mode operand (csrc/strict_kernels.cuh: SPL)
+
+
 def split_weight(w: torch.Tensor) -> torch.Tensor:
-    """fp32 [rows, K] -> bf16 [rows, 2, align8(K)]: plane 0 = bf16(w), plane 1 = bf16(w - plane 0); pad columns zero."""
+    """fp32 [rows, K] -> bf16 [rows, 3, align8(K)]: plane 0 = bf16(w), plane 1 = bf16(w - p0), plane 2 = bf16(w - p0 - p1)
+    (24 mantissa bits in total; the subtractions are exact in fp32); pad columns zero."""
     w = w.detach().to(torch.float32)
     rows, K = w.shape
     P = (K + 7) // 8 * 8
-    out = torch.zeros(rows, 2, P, dtype=torch.bfloat16, device=w.device)
-    hi = w.to(torch.bfloat16)
-    out[:, 0, :K] = hi
-    out[:, 1, :K] = (w - hi.float()).to(torch.bfloat16)
+    out = torch.zeros(rows, SPLIT_PLANES, P, dtype=torch.bfloat16, device=w.device)
+    r = w
+    for pl in range(SPLIT_PLANES):
+        h = r.to(torch.bfloat16)
+        out[:, pl, :K] = h
+        r = r - h.float()
     return out.contiguous()
 
 
@@ -418,6 +424,34 @@ def apply_rotary_pos_emb(x: torch.Tensor, sinu_pos) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# L2 residency of the pair stream (AF2_L2_PERSIST, default off until measured -- see DESIGN.md)
+# --------------------------------------------------------------------------------------------------
+L2_PERSIST = float(_os.environ.get("AF2_L2_PERSIST", "0") or 0)     # 0: off; (0, 1]: hit ratio of the window over x
+
+
+class l2_resident:
+    """with l2_resident(x): kernels launched on the current stream keep x's address range persisting in L2."""
+
+    def __init__(self, t: Optional[torch.Tensor]):
+        self.t = t if (L2_PERSIST > 0 and t is not None and t.is_cuda) else None
+
+    def __enter__(self):
+        if self.t is not None:
+            try:
+                _lib.check(_lib.load().af2_l2_persist(self.t.data_ptr(), self.t.numel() * self.t.element_size(), float(L2_PERSIST), _stream_ptr()))
+            except RuntimeError as e:
+                import sys
+                print(f"[alphafold2_b200] L2 persistence not applied: {e}", file=sys.stderr)
+                self.t = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            _lib.check(_lib.load().af2_l2_persist(None, 0, 0.0, _stream_ptr()))
+        return False
+
+
+# --------------------------------------------------------------------------------------------------
 # pre- / post-trunk glue (SURVEY.md 8f n1)
 # --------------------------------------------------------------------------------------------------
 def _w32(t: torch.Tensor) -> torch.Tensor:
@@ -480,15 +514,15 @@ def layernorm_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps
 
 def gemm_split(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Strict-mode building block: a [batch, M, K] x b [batch, N, K] fp32 -> [batch, M, N] fp32 through split-bf16 operands
-    (three tensor-core passes, fp32 accumulate)."""
+    (three bf16 planes per operand, six tensor-core passes, fp32 accumulate)."""
     _require(a, torch.float32, "a")
     _require(b, torch.float32, "b")
     batch, M, K = a.shape
     N = b.shape[1]
     P = (K + 7) // 8 * 8
     lib = _lib.load()
-    a_s = torch.empty(batch * M, 2, P, dtype=torch.bfloat16, device=a.device)
-    b_s = torch.empty(batch * N, 2, P, dtype=torch.bfloat16, device=a.device)
+    a_s = torch.empty(batch * M, SPLIT_PLANES, P, dtype=torch.bfloat16, device=a.device)
+    b_s = torch.empty(batch * N, SPLIT_PLANES, P, dtype=torch.bfloat16, device=a.device)
     _lib.check(lib.af2_split_bf16(a.data_ptr(), a_s.data_ptr(), batch * M, K, _stream_ptr()))
     _lib.check(lib.af2_split_bf16(b.data_ptr(), b_s.data_ptr(), batch * N, K, _stream_ptr()))
     ldc = (N + 3) // 4 * 4

@@ -177,14 +177,15 @@ int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const voi
 
 /* ======================================================================================================================
  * STRICT precision mode (alphafold2_b200.set_precision(model, "strict")): the same modules with fp32 activations between
- * kernels and split-bf16 operands on the tensor cores (v = hi + lo; hi*lo + lo*hi + hi*hi accumulated in fp32, ~16
- * mantissa bits per operand), so that results match the reference's fp32 path inside the north star's rtol 1e-3 /
- * atol 1e-4.  Split weights: bf16 [rows][2][align8(cols)] (hi plane | lo plane per row), built by ops.split_weight().
+ * kernels and split-bf16 operands on the tensor cores (v = p0 + p1 + p2, three bf16 planes = 24 mantissa bits; the six
+ * products down to 2^-24 accumulated in fp32), so that results match the reference's fp32 path inside the north star's
+ * rtol 1e-3 / atol 1e-4 also after 12 blocks.  Split weights: bf16 [rows][3][align8(cols)] (plane-major per row), built by
+ * ops.split_weight().
  * ====================================================================================================================== */
 typedef struct {
   const float* ln_gamma; const float* ln_beta;        /* FeedForward.norm                                   */
-  const void* w1; const float* b1;                    /* net.0  split [2*hid][2][align8(d)], fp32 [2*hid]    */
-  const void* w2; const float* b2;                    /* net.3  split [d][2][align8(hid)],   fp32 [d]        */
+  const void* w1; const float* b1;                    /* net.0  split [2*hid][3][align8(d)], fp32 [2*hid]    */
+  const void* w2; const float* b2;                    /* net.3  split [d][3][align8(hid)],   fp32 [d]        */
 } af2_ff_weights_strict;
 long long af2_feed_forward_strict_workspace(long long tokens, int d, int hidden);
 int af2_feed_forward_strict(const af2_ff_weights_strict* w, float* x, long long tokens, int d, int hidden, void* workspace,
@@ -192,8 +193,8 @@ int af2_feed_forward_strict(const af2_ff_weights_strict* w, float* x, long long 
 
 typedef struct {
   const float* ln_gamma; const float* ln_beta;        /* AxialAttention.norm                                              */
-  const void* w_qkvg; const float* b_qkvg;            /* [to_q * dim_head^-0.5 ; to_kv ; gating] split [4I][2][align8(d)], bias [4I] (zeros | gating.bias) */
-  const void* w_out; const float* b_out;              /* attn.to_out split [d][2][align8(I)], fp32 [d]                    */
+  const void* w_qkvg; const float* b_qkvg;            /* [to_q * dim_head^-0.5 ; to_kv ; gating] split [4I][3][align8(d)], bias [4I] (zeros | gating.bias) */
+  const void* w_out; const float* b_out;              /* attn.to_out split [d][3][align8(I)], fp32 [d]                    */
   const float* w_edge;                                /* edges_to_attn_bias.0.weight fp32 [H][d] or NULL                  */
 } af2_attn_weights_strict;
 long long af2_axial_attention_strict_workspace(int B, int h, int w, int d, int heads, int dim_head, int row_attn);
@@ -203,9 +204,9 @@ int af2_axial_attention_strict(const af2_attn_weights_strict* w, float* x, const
 
 typedef struct {
   const float* ln_gamma; const float* ln_beta;        /* norm                                                                          */
-  const void* w5; const float* b5;                    /* [left_proj; right_proj; left_gate; right_gate; out_gate] split [5d][2][align8(d)], fp32 [5d] */
+  const void* w5; const float* b5;                    /* [left_proj; right_proj; left_gate; right_gate; out_gate] split [5d][3][align8(d)], fp32 [5d] */
   const float* on_gamma; const float* on_beta;        /* to_out_norm                                                                   */
-  const void* w_out; const float* b_out;              /* to_out split [d][2][align8(d)], fp32 [d]                                      */
+  const void* w_out; const float* b_out;              /* to_out split [d][3][align8(d)], fp32 [d]                                      */
 } af2_trimul_weights_strict;
 long long af2_triangle_multiply_strict_workspace(int B, int N, int d);
 int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, const unsigned char* mask, int B, int N, int d,
@@ -213,8 +214,8 @@ int af2_triangle_multiply_strict(const af2_trimul_weights_strict* w, float* x, c
 
 typedef struct {
   const float* ln_gamma; const float* ln_beta;        /* norm                                                       */
-  const void* w_lr; const float* b_lr;                /* [left_proj; right_proj] split [2d][2][align8(d)], fp32 [2d] */
-  const void* w_out; const float* b_out;              /* proj_out split [d][2][align8(d)], fp32 [d]                 */
+  const void* w_lr; const float* b_lr;                /* [left_proj; right_proj] split [2d][3][align8(d)], fp32 [2d] */
+  const void* w_out; const float* b_out;              /* proj_out split [d][3][align8(d)], fp32 [d]                 */
 } af2_outer_weights_strict;
 long long af2_outer_mean_strict_workspace(int B, int S, int N, int d);
 int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
@@ -237,6 +238,10 @@ int af2_embed_pair_init(const long long* seq, const long long* msa, const float*
                         long long workspace_bytes, af2_stream_t stream);
 int af2_distogram_head(const float* x, const float* gamma, const float* beta, const float* w, const float* bias, float* out, int B,
                        int n, int d, int buckets, af2_stream_t stream);
+
+/* L2 residency hint for the fp32 pair stream: every kernel launched on `stream` afterwards treats [ptr, ptr + bytes) as
+ * persisting in L2 (cudaAccessPolicyWindow; clipped to the device's set-aside / window limits).  ptr == NULL clears it. */
+int af2_l2_persist(const void* ptr, long long bytes, float hit_ratio, af2_stream_t stream);
 
 #ifdef __cplusplus
 }
