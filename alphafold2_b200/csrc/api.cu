@@ -71,6 +71,20 @@ inline int x_hint(long long tokens, int d) {
   return (g_x_evict_last && mb >= 48.0 && mb <= 100.0) ? 1 : 0;
 }
 
+// Programmatic dependent launch (common.cuh): AF2_PDL=0 launches without the attribute (then wait / launch_dependents are no-ops)
+int g_pdl = 1;
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 struct NvtxRange {   // one NVTX range per C-ABI call (sub-op granularity for nsys / ncu --nvtx)
   explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
   ~NvtxRange() { nvtxRangePop(); }
@@ -199,8 +213,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   const double bytes = p.batch * ((double)p.M * p.K * 2 + (p.batch > 1 ? (double)p.N * p.K * 2 : 0) + (double)p.M * p.N * obytes) +
                        (p.batch > 1 ? 0 : (double)p.N * p.K * 2);
   ProfScope ps(s, p.batch > 1 ? KC_GEMM_CHANNEL : KC_GEMM_LINEAR, flops, bytes);
-  kern<<<grid, GEMM_THREADS, L::TOTAL, s>>>(ta, tb, tc, tr, p);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, s, ta, tb, tc, tr, p));
   return AF2_OK;
 }
 
@@ -409,8 +422,8 @@ int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_b
   const long long cap = (long long)sm_count() * 3;     // persistent: 3 resident blocks per SM
   const int grid = (int)(need < cap ? need : cap);
   ProfScope ps(s, KC_LAYERNORM, 0.0, (double)T * d * 4 + (double)T * heads * 2);
-  if (mma && d == 256) pair_bias_mma_kernel<16><<<grid, 256, 0, s>>>(p);
-  else if (mma) pair_bias_mma_kernel<8><<<grid, 256, 0, s>>>(p);
+  if (mma && d == 256) CUDA_OK(launch_pdl(pair_bias_mma_kernel<16>, dim3(grid), dim3(256), 0, s, p));
+  else if (mma) CUDA_OK(launch_pdl(pair_bias_mma_kernel<8>, dim3(grid), dim3(256), 0, s, p));
   else {
     switch (d / 32) {
       case 7: pair_bias_kernel<7><<<grid, 256, 0, s>>>(p); break;
@@ -452,8 +465,7 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
   const long long tiles = (T + C2T_TOK - 1) / C2T_TOK;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   ProfScope ps(s, KC_CHAN2TOK, 0.0, (double)T * D * (p.mode == 0 ? 8.0 : 6.0));
-  kern<<<grid, L::THREADS, L::TOTAL, s>>>(tx, tg, ty, q);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(launch_pdl(kern, dim3(grid), dim3(L::THREADS), L::TOTAL, s, tx, tg, ty, q));
   return AF2_OK;
 }
 
@@ -522,8 +534,7 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   const double tokens = (double)p.n * p.nbatch;
   ProfScope ps(s, KC_ATTENTION, 4.0 * tokens * p.n * p.heads * DH,
                tokens * p.heads * DH * 2.0 * 5 + (p.has_bias ? (double)p.heads * p.n * p.n * 2 : 0));
-  kern<<<grid, ATTN_THREADS, L::TOTAL, s>>>(tq, tk, tv, tbias, tg, to, p);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(launch_pdl(kern, dim3(grid), dim3(ATTN_THREADS), L::TOTAL, s, tq, tk, tv, tbias, tg, to, p));
   return AF2_OK;
 }
 
@@ -657,6 +668,7 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_GATHER_FUSED")) g_gather_fused = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_GROUP")) g_attn_group = atoi(e) != 0;
   if (const char* e = getenv("AF2_X_EVICT_LAST")) g_x_evict_last = atoi(e) != 0;
+  if (const char* e = getenv("AF2_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_TRACE")) {
     if (atoi(e) != 0 && !g_proj_trace) {
       if (cudaMalloc(&g_proj_trace, 2048 * sizeof(long long)) != cudaSuccess) g_proj_trace = nullptr;

@@ -78,6 +78,8 @@ chan_to_token_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   if (p.mode == 0)
     for (int i = threadIdx.x; i < D; i += L::THREADS) { aff[i] = p.gamma[i]; aff[D + i] = p.beta[i]; }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ================================

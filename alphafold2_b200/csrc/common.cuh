@@ -186,6 +186,19 @@ __device__ __forceinline__ float2 ldg_f2_hint(const float2* p, uint64_t pol) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every persistent kernel of the block is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and
+//   * signals `launch_dependents` right after its own set-up: the NEXT kernel's CTAs are then scheduled onto an SM the moment
+//     this kernel's CTA leaves it (instead of after the whole grid has drained + a launch latency) and run THEIR set-up
+//     (mbarrier init, TMEM allocation, tensor-map prefetch) in the shadow of this kernel's tail;
+//   * executes `wait` before its first access to global memory that a predecessor may have written (or still reads): the wait
+//     returns only when all prerequisite grids have completed and flushed, so the stream's data dependences are unchanged.
+// Both are no-ops for a launch without the attribute.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -206,6 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = p.num_ntiles;

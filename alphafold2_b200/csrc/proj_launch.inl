@@ -76,9 +76,10 @@ int launch_proj_inst(const CUtensorMap& tb, const CUtensorMap* tc, const CUtenso
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * CTAS, 1, 1); cfg.blockDim = dim3(PROJ_THREADS, 1, 1); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tb, tc[0], tc[1], tc[2], tx, p));
   return AF2_OK;
 }

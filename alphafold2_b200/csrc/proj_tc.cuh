@@ -488,6 +488,8 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // ---- work decomposition: item = (row unit of 128*CTAS rows, column chunk) ----
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, 2) pair_bias_mma_kernel(const PairBiasPar
   }
   const int groups = static_cast<int>((p.T + 15) / 16);
   const uint64_t pol = l2_policy(p.x_evict_last != 0);
+  pdl_wait();            // (the w_edge fragments above are weights: safe to load before the predecessor has finished)
   for (int gi = warp_global; gi < groups; gi += nwarps) {
     const long long r0 = static_cast<long long>(gi) * 16 + g, r1 = r0 + 8;
     const bool l0 = r0 < p.T, l1 = r1 < p.T;
