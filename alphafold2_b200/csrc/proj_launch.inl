@@ -20,7 +20,8 @@ int g_proj_ctas = 2;
 int g_proj_wide = 1;              // 1: 64-column epilogue steps where the segment width allows (AF2_PROJ_WIDE)
 int g_proj_balance = 1;           // 1: equal (row unit, column tile) ranges per cluster; 0: round-robin items (AF2_PROJ_BALANCE)
 long long* g_proj_trace = nullptr; // device buffer of 1024 stamps when AF2_PROJ_TRACE=1 (debug only)
-int g_proj_l2pf = 1;              // 1: producer warps prefetch the next item's rows into L2 (AF2_PROJ_L2PF)
+int g_proj_l2pf = 0;              // 1: producer warps prefetch the next item's rows into L2 (AF2_PROJ_L2PF); measured -0.5..-1 % when off
+                                 // (two same-box A/Bs, profiles/r02_ab_*.log): the prefetched lines are evicted by the kernel's own output stream
 double g_proj_prod_tiles = 4.0;   // cost of producing one A tile in units of one 256-column MMA tile (AF2_PROJ_PRODTILES)
 
 // can this LN -> Linear cluster run on the fused kernel?

@@ -40,7 +40,7 @@ def main():
         xg, mg = gt(x.cuda(), m.cuda(), cu(mask), cu(msa_mask))
         xg2, mg2 = gt((x * 1.0).cuda(), (m * 1.0).cuda(), cu(mask), cu(msa_mask))
         torch.cuda.synchronize()
-        gt.graph, gt.outputs, gt.inputs = None, None, None      # a live graph with NCCL nodes makes the teardown hang
+        gt.release()                                              # (teardown would do it too: parallel._hook_teardown)
         res = {"rank": rank, "world": world, "cfg": [d, H, dh, N, S, masked],
                "x_vs_single": (xs - x1).abs().max().item(), "m_vs_single": (ms - m1_).abs().max().item(),
                "x_scale": x1.abs().max().item(), "m_scale": m1_.abs().max().item(),

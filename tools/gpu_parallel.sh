@@ -1,6 +1,23 @@
 #!/bin/bash
-# 2-GPU check of the sharded trunk + scaling bench at N=2 (a 2-GPU gpurun call is charged twice its wall time: keep the timeouts tight)
+# N-GPU check of the sharded trunk + scaling bench (an N-GPU gpurun call is charged N x its wall time: keep the timeouts tight)
+# usage: tools/gpu_parallel.sh <N> <tag> [C4]
+N=${1:-2}; TAG=${2:-r02}; BIG=${3:-}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parallel.py -q -m gpu -x --timeout 200 -p no:cacheprovider 2>&1 | tail -8
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 tests/parallel_check_multi_gpu.py > gpurun_out/parallel_check.log 2>&1; echo "parallel_check rc=$?"; grep -E '^\{' gpurun_out/parallel_check.log | head -12; tail -5 gpurun_out/parallel_check.log | grep -v '^{'
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo "bench2 rc=$?"; tail -c 1500 gpurun_out/bench_2gpu.json; tail -3 gpurun_out/bench_2gpu.err
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 240 $TR --master-port 29551 tests/parallel_check_multi_gpu.py > gpurun_out/parallel_check_${N}gpu_${TAG}.log 2>&1; echo "parallel_check rc=$?"
+grep -E '^\{' gpurun_out/parallel_check_${N}gpu_${TAG}.log | cut -c1-330 | head -6; grep -v '^{' gpurun_out/parallel_check_${N}gpu_${TAG}.log | tail -4
+timeout 200 $TR --master-port 29552 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_C2_${N}gpu_${TAG}.json 2> gpurun_out/bench_C2_${N}gpu_${TAG}.err; echo "bench C2 N=$N rc=$?"; tail -2 gpurun_out/bench_C2_${N}gpu_${TAG}.err
+AF2_GATHER_FUSED=0 timeout 200 $TR --master-port 29553 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_C2_${N}gpu_pieces_${TAG}.json 2> /dev/null; echo "bench C2 N=$N (per-piece launches) rc=$?"
+if [ -n "$BIG" ]; then
+  timeout 300 $TR --master-port 29554 bench.py --gpus $N --steps 5 --warmup 3 --workload C4 --no-cpu-baseline > gpurun_out/bench_C4_${N}gpu_${TAG}.json 2> gpurun_out/bench_C4_${N}gpu_${TAG}.err; echo "bench C4 N=$N rc=$?"; tail -2 gpurun_out/bench_C4_${N}gpu_${TAG}.err
+fi
+python - <<PY
+import json, glob
+for f in sorted(glob.glob('gpurun_out/bench_C*_${N}gpu*_${TAG}.json')):
+    try:
+        d = json.load(open(f))
+        print(f.split('/')[-1], 'ms_per_step', round(d['ms_per_step'], 3), 'value', round(d['value']), 'launches', d['gpu_launches'], d.get('schedule'),
+              [(k['name'][:10], k['launches_per_step'], round(k['ms_per_step'], 2)) for k in d['kernel_classes']])
+    except Exception as e:
+        print(f, 'unreadable', e)
+PY
