@@ -63,6 +63,34 @@ def cols_to_rows(t_col: torch.Tensor, group) -> torch.Tensor:
     return recv.permute(1, 0, 2, 3).reshape(R, P * Cl, d)
 
 
+class _Deferred:
+    """cols_to_rows on a side stream: the MSA tensor goes back to row shards while the pair track of the same block runs
+    (nothing reads it before the next block's row attention).  The collective itself runs on the process group's NCCL
+    stream either way; what the side stream removes is the main stream's wait for it.  `get()` joins."""
+
+    def __init__(self, t_col: torch.Tensor, group, side):
+        P = dist.get_world_size(group)
+        RR, Cl, d = t_col.shape
+        R = RR // P
+        self.keep = t_col                                                     # source stays alive until the side stream is done
+        send = t_col.contiguous().view(P, R, Cl, d)
+        recv = torch.empty_like(send)                                         # allocated on the main stream: its pool, its ordering
+        self.out = torch.empty(R, P * Cl, d, dtype=t_col.dtype, device=t_col.device)
+        self.bufs = (send, recv)
+        cur = torch.cuda.current_stream()
+        ready = cur.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            dist.all_to_all_single(recv, send, group=group)
+            self.out.view(R, P, Cl, d).copy_(recv.permute(1, 0, 2, 3))
+            self.done = side.record_event()
+
+    def get(self) -> torch.Tensor:
+        torch.cuda.current_stream().wait_event(self.done)
+        out, self.keep, self.bufs = self.out, None, None
+        return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # stage ops on the GPU (C ABI)
 # ------------------------------------------------------------------------------------------------------------
@@ -183,11 +211,17 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
             g = all_gather_cat0(b.transpose(0, 1).contiguous(), group)   # [N, H, npad] rows in global order
             return g.transpose(0, 1).contiguous()                    # [H, N, npad]
 
+        overlap = OVERLAP_MSA_RETURN and x_row.is_cuda and P > 1
+        side = torch.cuda.Stream() if overlap else None
+        pending = None
         for block in evo.layers:
             pair, ff, msa_attn, msa_ff = block.layer
             d = x_row.shape[-1]
             # --- MSA track (alphafold2.py:438-439) ---
-            ops.axial_attention_(msa_attn.row_attn, m_row, gathered_bias(msa_attn.row_attn, x_row), mm_rows, True)
+            bias_m = gathered_bias(msa_attn.row_attn, x_row)
+            if pending is not None:
+                m_row, pending = pending.get(), None
+            ops.axial_attention_(msa_attn.row_attn, m_row, bias_m, mm_rows, True)
             m_col = rows_to_cols(m_row, group)                                           # [S, N/P, d]
             ops.axial_attention_(msa_attn.col_attn, m_col, None, mm_cols, False)
             ops.feed_forward_(msa_ff, m_col)
@@ -195,7 +229,10 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
             LR = ops.outer_project(pair.outer_mean, m_col, mm_cols)                      # [2d, S, pitch(N/P)]
             Rg = all_gather_cat0(LR[d:], group)                                          # [P*d, S, pitch]
             ops.outer_contract_(pair.outer_mean, x_row, LR[:d], Rg, mm_full, r * Rn, P)
-            m_row = cols_to_rows(m_col, group)
+            if overlap:
+                pending = _Deferred(m_col, group, side)                                  # joins at the next block's row attention
+            else:
+                m_row = cols_to_rows(m_col, group)
             # --- triangle multiply outgoing on pair rows (alphafold2.py:381) ---
             tm = pair.triangle_multiply_outgoing
             L, R, G = ops.tri_project(tm, x_row, mask_rows)
@@ -218,6 +255,8 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
             ops.feed_forward_(ff, x_col)
             x_row = cols_to_rows(x_col, group)
 
+        if pending is not None:
+            m_row, pending = pending.get(), None
         if not gather_output:
             return x_row, m_row
         xo = all_gather_cat0(x_row, group)[None]
@@ -228,6 +267,7 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
 COLLECTIVES_PER_BLOCK = {"all_gather_small_bias": 3, "all_gather_operand": 3, "all_to_all_msa": 2, "all_to_all_pair": 4}
 
 
+OVERLAP_MSA_RETURN = True     # the MSA tensor's all-to-all back to row shards runs beside the pair track (side stream)
 GRAPH_ENABLED = True     # module switch: set False to force the eager schedule (bench.py does, around its per-launch profiling pass)
 
 _LIVE_GRAPHS = weakref.WeakSet()
