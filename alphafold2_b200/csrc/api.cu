@@ -582,7 +582,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
 
 // OuterMean normaliser of pair rows [row0, row0 + rows) of one batch element (quirk Q3): bit-packed kernel when the packed
 // mask fits in shared memory, else the byte-loop kernel
-int launch_outer_scale(const uint8_t* mask, float* scale, int row0, int rows, int S, int N, float eps, cudaStream_t s);
+int launch_outer_scale(const uint8_t* mask, float* scale, uint32_t* words, int row0, int rows, int S, int N, float eps, cudaStream_t s);
 
 int ew_grid(long long n) {
   long long b = (n + 255) / 256;
@@ -590,20 +590,23 @@ int ew_grid(long long n) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-int launch_outer_scale(const uint8_t* mask, float* scale, int row0, int rows, int S, int N, float eps, cudaStream_t s) {
+int launch_outer_scale(const uint8_t* mask, float* scale, uint32_t* words, int row0, int rows, int S, int N, float eps, cudaStream_t s) {
   const long long T = (long long)rows * N;
   if (T <= 0) return AF2_OK;
-  const size_t smem = (size_t)((S + 31) / 32) * N * 4;
+  const int nw = (S + 31) / 32;
+  const size_t smem = (size_t)nw * N * 4;
   ProfScope ps(s, KC_MISC, 0.0, 0.0);
-  if (smem <= 160 * 1024) {
+  if (words && smem <= 160 * 1024) {
     static size_t configured[MAX_DEVICES] = {0};
     if (smem > 48 * 1024 && smem > configured[cur_dev()]) {
       CUDA_OK(cudaFuncSetAttribute(outer_scale_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[cur_dev()] = smem;
     }
+    mask_pack_bits_kernel<<<ew_grid((long long)nw * N), 256, 0, s>>>(mask, words, S, N);
+    CUDA_OK(cudaGetLastError());
     const long long need = (T + 255) / 256;
     const int grid = (int)(need < sm_count() ? need : sm_count());
-    outer_scale_bits_kernel<<<grid, 256, smem, s>>>(mask, scale, row0, rows, S, N, eps);
+    outer_scale_bits_kernel<<<grid, 256, smem, s>>>(words, scale, row0, rows, S, N, eps);
   } else {
     outer_scale_rows_kernel<<<ew_grid(T), 256, 0, s>>>(mask, scale, row0, rows, S, N, eps);
   }
@@ -933,7 +936,7 @@ long long af2_outer_mean_workspace(int B, int S, int N, int d) {
   const long long np8 = align_up(N, 8), np4 = align_up(N, 4);
   return align_up(Tm * d * 2, 256) + align_up((long long)2 * d * B * S * np8 * 2, 256) +
          align_up((long long)d * B * N * np4 * 4, 256) + align_up(Tx * d * 2, 256) + align_up(Tm * 4, 256) +
-         align_up(Tx * 4, 256) + 1024;
+         align_up(Tx * 4, 256) + align_up((long long)((S + 31) / 32) * N * 4, 256) + 1024;
 }
 
 int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
@@ -953,6 +956,7 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
   __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Tx * d);
   float* maskf = ar.take<float>(Tm);
   float* scale = ar.take<float>(Tx);
+  uint32_t* mwords = ar.take<uint32_t>((long long)((S + 31) / 32) * N);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_mean: workspace too small");
 
   const bool fused_front = g_proj_ctas > 0 && w->w_cat && proj_dim_ok(d) && np8 == N;
@@ -964,7 +968,7 @@ int af2_outer_mean(const af2_outer_weights* w, float* x, const float* m, const u
     if (!fused_front) { ProfScope ps(s, KC_MISC, 0.0, 0.0); mask_to_float_kernel<<<ew_grid(Tm), 256, 0, s>>>(msa_mask, maskf, Tm); }
     CUDA_OK(cudaGetLastError());
     for (int b = 0; b < B; ++b)
-      AF2_TRY(launch_outer_scale(msa_mask + (long long)b * S * N, scale + (long long)b * N * N, 0, N, S, N, eps, s));
+      AF2_TRY(launch_outer_scale(msa_mask + (long long)b * S * N, scale + (long long)b * N * N, mwords, 0, N, S, N, eps, s));
   }
   if (np8 != N) CUDA_OK(cudaMemsetAsync(LRc, 0, (size_t)2 * d * cs_lr * 2, s));
   // [left | right] = (LN(m) W^T + b) * mask  -> channel-major [c][b*S + s][i]
@@ -1225,7 +1229,7 @@ int af2_outer_project(const af2_outer_weights* w, const float* m, const unsigned
 
 long long af2_outer_contract_workspace(int rows, int N, int d) {
   return align_up((long long)d * rows * align_up(N, 4) * 4, 256) + align_up((long long)rows * N * d * 2, 256) +
-         align_up((long long)rows * N * 4, 256) + 1024;
+         align_up((long long)rows * N * 4, 256) + align_up((long long)N * 4096 / 8, 256) + 1024;    // + packed mask bits (S <= 4096)
 }
 
 // x [rows, N, d] (pair rows row0..row0+rows, updated in place) += proj_out( sum_s L[s][i] R[s][j] * scale[i][j] )
@@ -1244,8 +1248,9 @@ int af2_outer_contract(const af2_outer_weights* w, float* x, const void* Lc, lon
   float* Oc = ar.take<float>(d * cs_o);
   __nv_bfloat16* tn = ar.take<__nv_bfloat16>(T * d);
   float* scale = ar.take<float>(T);
+  uint32_t* mwords = (S <= 4096) ? ar.take<uint32_t>((long long)((S + 31) / 32) * N) : nullptr;
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_contract: workspace too small");
-  if (msa_mask_full) AF2_TRY(launch_outer_scale(msa_mask_full, scale, row0, rows, S, N, eps, s));
+  if (msa_mask_full) AF2_TRY(launch_outer_scale(msa_mask_full, scale, mwords, row0, rows, S, N, eps, s));
   const __nv_bfloat16* L = static_cast<const __nv_bfloat16*>(Lc);
   const __nv_bfloat16* R = static_cast<const __nv_bfloat16*>(Rg);
   const int pc = N / pieces;

@@ -453,20 +453,25 @@ __global__ void outer_scale_rows_kernel(const uint8_t* __restrict__ mask, float*
 }
 
 // Bit-packed version of both kernels above: count[i][j] = popc(bits_i & bits_j) with bits_i = the S mask bits of residue i.
-// Every block first packs the whole [S][N] byte mask into shared memory as words[w][i] (w = s / 32; coalesced byte reads,
-// the mask is at most a few hundred KB and L2-resident), then walks its (i, j) pairs: the i-word is a broadcast, the j-words
-// are consecutive -> conflict-free.  S / 32 AND+POPC steps per pair instead of S byte-pair loads (17.6 us -> a few us at C2).
-__global__ void __launch_bounds__(256) outer_scale_bits_kernel(const uint8_t* __restrict__ mask, float* __restrict__ scale,
-                                                               int row0, int rows, int S, int N, float eps) {
-  extern __shared__ uint32_t bits[];                 // [words][N]
-  const int words = (S + 31) >> 5;
-  for (int idx = threadIdx.x; idx < words * N; idx += blockDim.x) {
+//   mask_pack_bits_kernel: words[w][i] (w = s / 32) <- the [S][N] byte mask, once per call (coalesced byte reads over i);
+//   outer_scale_bits_kernel: every block copies the packed words (S/32 * N * 4 bytes, L2 resident) into shared memory and
+//   walks its (i, j) pairs: the i-word is a broadcast, the j-words are consecutive -> conflict-free.  S / 32 AND+POPC steps
+//   per pair instead of S byte-pair loads (C2: 17.6 us -> ~4 us; the first version packed inside every block: 150 us at C4).
+__global__ void __launch_bounds__(256) mask_pack_bits_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ words, int S, int N) {
+  const int nw = (S + 31) >> 5;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nw * N; idx += gridDim.x * blockDim.x) {
     const int w = idx / N, i = idx - w * N;
     uint32_t v = 0;
     const int s1 = min(S, (w + 1) * 32);
     for (int s = w * 32; s < s1; ++s) v |= (mask[static_cast<long long>(s) * N + i] != 0 ? 1u : 0u) << (s & 31);
-    bits[idx] = v;
+    words[idx] = v;
   }
+}
+__global__ void __launch_bounds__(256) outer_scale_bits_kernel(const uint32_t* __restrict__ words, float* __restrict__ scale,
+                                                               int row0, int rows, int S, int N, float eps) {
+  extern __shared__ uint32_t bits[];                 // [words][N]
+  const int nw = (S + 31) >> 5;
+  for (int idx = threadIdx.x; idx < nw * N; idx += blockDim.x) bits[idx] = words[idx];
   __syncthreads();
   const long long total = static_cast<long long>(rows) * N;
   const float fS = static_cast<float>(S);
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(256) outer_scale_bits_kernel(const uint8_t* __
     const int j = static_cast<int>(idx % N);
     const int i = row0 + static_cast<int>(idx / N);
     int cnt = 0;
-    for (int w = 0; w < words; ++w) cnt += __popc(bits[w * N + i] & bits[w * N + j]);
+    for (int w = 0; w < nw; ++w) cnt += __popc(bits[w * N + i] & bits[w * N + j]);
     scale[idx] = 1.0f / (fS * (static_cast<float>(cnt) + eps));
   }
 }

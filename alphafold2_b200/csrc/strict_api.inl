@@ -272,7 +272,7 @@ long long af2_outer_mean_strict_workspace(int B, int S, int N, int d) {
   const int P8 = a8(N);
   return align_up(Tm * SPL * a8(d) * 2, 256) + align_up(Tm * 2 * d * 4, 256) + align_up((long long)2 * d * SPL * S * P8 * 2, 256) +
          align_up((long long)d * N * align_up(N, 4) * 4, 256) + align_up((long long)N * N * SPL * a8(d) * 2, 256) +
-         align_up((long long)N * N * 4, 256) + 2048;
+         align_up((long long)N * N * 4, 256) + align_up((long long)((S + 31) / 32) * N * 4, 256) + 2048;
 }
 
 int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const float* m, const unsigned char* msa_mask, int B, int S,
@@ -292,6 +292,7 @@ int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const flo
   float* Oc = ar.take<float>((long long)d * N * np4);
   __nv_bfloat16* tn = ar.take<__nv_bfloat16>(Txb * SPL * Pd);
   float* scale = ar.take<float>(Txb);
+  uint32_t* mwords = ar.take<uint32_t>((long long)((S + 31) / 32) * N);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "outer_mean_strict: workspace too small");
   AF2_TRY(strict_ln_split(m, w->ln_gamma, w->ln_beta, ms, Tm, d, s));
   AF2_TRY(strict_linear_f32(ms, w->w_lr, w->b_lr, p2, Tm, 2 * d, d, s));
@@ -304,7 +305,7 @@ int af2_outer_mean_strict(const af2_outer_weights_strict* w, float* x, const flo
     GemmCall c = split_call(LRc, P8, (long long)S * P8, cs, LRc + (long long)d * cs, P8, (long long)S * P8, cs, N, N, S, d, true);
     c.mode = EPI_STORE_F32; c.layout = LAYOUT_TOKEN; c.out = Oc; c.ld_out = np4; c.out_batch = (long long)N * np4;
     AF2_TRY(launch_gemm(c, s));
-    if (mb) AF2_TRY(launch_outer_scale(mb, scale, 0, N, S, N, eps, s));
+    if (mb) AF2_TRY(launch_outer_scale(mb, scale, mwords, 0, N, S, N, eps, s));
     StrictC2TParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.src = Oc; cp.chan_stride = (long long)N * np4; cp.pitch = np4; cp.rows = N; cp.n = N; cp.d = d; cp.P = Pd; cp.mode = 1;
