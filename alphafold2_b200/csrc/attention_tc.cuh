@@ -34,6 +34,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef AF2_ATTN_POLY_EXP
+#define AF2_ATTN_POLY_EXP 1      // 0: every softmax exponential on the MUFU (A/B reference build)
+#endif
+
 namespace af2 {
 
 struct AttnParams {
@@ -527,7 +531,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float a0, a1, b0, b1;
         unpack2(add2(pack2(s[k], s[k + 1]), nm2), a0, a1);
         unpack2(add2(pack2(s[k + 2], s[k + 3]), nm2), b0, b1);
+#if AF2_ATTN_POLY_EXP
+        // every second exponential on the FMA pipe (common.cuh: exp2_poly2), the others on the MUFU
+        const float e0 = fast_exp2(a0), e2 = fast_exp2(b0);
+        float e1, e3;
+        unpack2(exp2_poly2(pack2(fmaxf(a1, -126.0f), fmaxf(b1, -126.0f))), e1, e3);
+#else
         const float e0 = fast_exp2(a0), e1 = fast_exp2(a1), e2 = fast_exp2(b0), e3 = fast_exp2(b1);
+#endif
         lsa = add2(lsa, pack2(e0, e1));
         lsb = add2(lsb, pack2(e2, e3));
         pk[k >> 1] = pack_bf16x2(e0, e1);

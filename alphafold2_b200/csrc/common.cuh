@@ -271,6 +271,28 @@ __device__ __forceinline__ f32x2 sigmoidf_fast2(f32x2 x) {
   return pack2(ra, rb);
 }
 
+// 2^x for two values on the FMA pipe (no MUFU): round-to-nearest split x = i + f (|f| <= 0.5) by the 1.5 * 2^23 magic
+// constant, degree-4 polynomial for 2^f (max rel. error 4.2e-5 -- the result is rounded to bf16, 2^-9), exponent inserted by
+// an integer add: (as_int(t) << 23) keeps exactly i << 23 because the magic constant's low 9 bits are zero.  Used by the
+// attention softmax for every second element: the 16 softmax warps of a key block all reach their exponentials at the same
+// time, and with one MUFU.EX2 per element that phase alone is 1024 cycles (16 results / clk / SM) of a ~3800-cycle block.
+// x must be >= -126 (the caller clamps; -inf logits of masked keys become 2^-126 ~ 1e-38, i.e. zero after the bf16 pack).
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const f32x2 t = add2(x, magic);
+  const f32x2 f = fma2(add2(t, nmagic), pack2(-1.0f, -1.0f), x);      // x - round(x), exact
+  f32x2 p = fma2(f, pack2(0.0096181291f, 0.0096181291f), pack2(0.0555041087f, 0.0555041087f));
+  p = fma2(p, f, pack2(0.2402265070f, 0.2402265070f));
+  p = fma2(p, f, pack2(0.6931471806f, 0.6931471806f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(p, p0, p1);
+  const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  return pack2(r0, r1);
+}
+
 // Four logistic values with ONE reciprocal.  The epilogues that apply sigmoid / GELU to whole accumulator tiles are bound by
 // the MUFU unit (16 results / clk / SM: ex2 + rcp per element = 4096 clk for a 128 x 256 tile against 2176 clk of tensor
 // work).  For a, b, c, d >= 1:  r = 1 / (a b c d)  ->  1/a = r (cd) b, ...: one MUFU.RCP and nine multiplies (five packed
