@@ -34,8 +34,12 @@
 #pragma once
 #include "common.cuh"
 
+// 1: every second softmax exponential by an FMA-pipe polynomial (common.cuh: exp2_poly2) instead of the MUFU.  Measured slower
+// (axial_attention class 4.50 vs 4.04 ms per C2 forward, C4 block 11.8 vs 11.0 ms, profiles/r02h_ab_poly_exp.log): the softmax
+// warps are bound by their own instruction stream (4 warps per scheduler, all in the same phase), not by MUFU throughput, so
+// the ~7 extra instructions per emulated element lengthen the critical path.  Kept as a build option, off.
 #ifndef AF2_ATTN_POLY_EXP
-#define AF2_ATTN_POLY_EXP 1      // 0: every softmax exponential on the MUFU (A/B reference build)
+#define AF2_ATTN_POLY_EXP 0
 #endif
 
 namespace af2 {
