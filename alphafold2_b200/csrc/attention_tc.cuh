@@ -242,9 +242,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&q_empty[gs], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[gs], L::Q_BYTES);
         tma_load_4d(smem + L::Q_OFF + gs * L::Q_BYTES, &tmQ, &q_full[gs], 0, qb * 128, h, b);
-        mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
-        tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
+        // (the gate tile of the item is loaded by the V producer warp: its slot is handed back by the epilogue of item
+        // it - 2, and waiting for that HERE delayed the K loads of the next item -- see the note there)
         const bool stream_bias = p.has_bias && !resident;
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
@@ -263,7 +262,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == ATTN_W_VPROD) {
-    // ================================ V producer ==================================
+    // ================================ V + gate producer ===========================
+    // The gate tile of item `it` is only needed by the item's epilogue, and its slot (it & 1) is released by the epilogue of
+    // item it - 2.  It used to be loaded by the Q/K producer right after Q: with two key blocks per item that wait sat in
+    // front of the K loads of the NEXT item, so S of every item's first block was issued one TMA round trip late (ncu:
+    // 31 % of the softmax warps' samples on the s_full wait, block period 3800 cycles for ~1000 cycles of tensor work).
+    // Here it follows the item's V loads, where it delays nothing.
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
@@ -275,6 +279,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
           tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
         }
+        const int gs = it & 1;
+        mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
+        tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
       }
     }
   } else if (warp == 1) {
