@@ -55,8 +55,10 @@ struct AttnParams {
   __nv_bfloat16* out;         // [token, heads*DH]
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
+  int l2_prefetch;            // 1: the K producer prefetches K / V / Q / gate boxes ATTN_PF_DIST key blocks ahead into L2 (AF2_ATTN_L2PF)
 };
 
+constexpr int ATTN_PF_DIST = 4;                    // L2 prefetch distance of the K producer, in key blocks
 constexpr int ATTN_NSPLIT = 4;                      // softmax threads per query row (each owns 128 / NSPLIT keys of a block)
 constexpr int ATTN_SM_WARPS = 4 * ATTN_NSPLIT;      // softmax warps 2 .. 2 + ATTN_SM_WARPS - 1
 constexpr int ATTN_W_KEYMASK = 2 + ATTN_SM_WARPS;   // then: key-mask warp, V TMA warp, 4 epilogue warps
@@ -223,6 +225,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
+      // L2 prefetch ATTN_PF_DIST key blocks ahead of the loads.  The K/V ring is only two stages deep when a bias is present
+      // (the resident bias tiles take the room of two more), so the load of block g + 2 is issued when block g's MMAs
+      // retire: with the operands coming from DRAM (~2 us under load) that round trip, not the tensor pipe or the softmax,
+      // set the block period.  Prefetched, the ring's loads hit L2.
+      auto prefetch_block = [&](int g) {
+        const int it2 = g / nkv, j2 = g - it2 * nkv;
+        if (it2 >= my_items || !p.l2_prefetch) return;
+        int qb2, h2, b2;
+        decode(it2, qb2, h2, b2);
+        tma_prefetch_4d(&tmK, 0, j2 * 128, h2, b2);
+        tma_prefetch_4d(&tmV, 0, j2 * 128, h2, b2);
+        if (j2 == 0) {
+          tma_prefetch_4d(&tmQ, 0, qb2 * 128, h2, b2);
+          tma_prefetch_4d(&tmG, 0, qb2 * 128, h2, b2);
+        }
+      };
+      for (int g = 0; g < ATTN_PF_DIST; ++g) prefetch_block(g);
       int prev_combo = -1, nc = 0;
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
@@ -248,6 +267,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
           const int kst = g % nst;
+          prefetch_block(g + ATTN_PF_DIST);
           // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
           mbar_wait(&k_empty[kst], ((g / nst) & 1) ^ 1);
           uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
