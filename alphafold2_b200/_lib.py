@@ -58,6 +58,7 @@ _SIGNATURES = {
     "af2_check_device": (ci, []),
     "af2_set_proj_mode": (None, [ci]),
     "af2_debug_proj_trace": (ci, [C.POINTER(C.c_longlong)]),
+    "af2_debug_attn_trace": (ci, [C.POINTER(C.c_longlong)]),
     "af2_launch_count": (C.c_ulonglong, []),
     "af2_profile_enable": (None, [ci]),
     "af2_profile_read": (ll, [ci, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -470,7 +470,8 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
-int g_attn_l2pf = 1;      // 1: attention K producer prefetches upcoming K / V / Q / gate boxes into L2 (AF2_ATTN_L2PF)
+long long* g_attn_trace = nullptr;   // device buffer of 1024 stamps when AF2_ATTN_TRACE=1 (debug only)
+int g_attn_l2pf = 0;      // 1: attention K producer prefetches upcoming K / V / Q / gate boxes into L2 (AF2_ATTN_L2PF)
 int g_attn_group = 1;     // 1: attention CTAs grouped per (h, b') unit for 2..8 query blocks (AF2_ATTN_GROUP=0: n > 256 ungrouped)
 int g_gather_fused = 1;   // 1: contractions over all-gathered operand pieces in ONE launch (AF2_GATHER_FUSED=0: one launch per piece)
 
@@ -575,6 +576,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.mask = mask; p.mask_sb = tok_sb; p.mask_si = tok_si;
   p.gate = gate; p.out = out; p.tok_sb = tok_sb; p.tok_si = tok_si; p.ld_gate = I; p.ld_out = I;
   p.l2_prefetch = g_attn_l2pf;
+  p.trace = g_attn_trace;
   if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
   if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
   return fail(AF2_ERR_BAD_ARG, "attention: dim_head %d unsupported (32 or 64)", dh);
@@ -661,6 +663,15 @@ int af2_debug_proj_trace(long long* out) {
   return AF2_OK;
 }
 
+// debug: copies the clock64 stamps of CTA 0 of the last attention launch (AF2_ATTN_TRACE=1) to `out` (1024 entries) and clears them
+int af2_debug_attn_trace(long long* out) {
+  if (!g_attn_trace) return fail(AF2_ERR_BAD_ARG, "attention trace not enabled (AF2_ATTN_TRACE=1)");
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, g_attn_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemset(g_attn_trace, 0, 1024 * sizeof(long long)));
+  return AF2_OK;
+}
+
 void af2_set_proj_mode(int ctas) { g_proj_ctas = ctas < 0 ? 2 : (ctas > 2 ? 2 : ctas); }
 
 int af2_check_device(void) {
@@ -673,6 +684,12 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_GATHER_FUSED")) g_gather_fused = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_GROUP")) g_attn_group = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_L2PF")) g_attn_l2pf = atoi(e) != 0;
+  if (const char* e = getenv("AF2_ATTN_TRACE")) {
+    if (atoi(e) != 0 && !g_attn_trace) {
+      if (cudaMalloc(&g_attn_trace, 1024 * sizeof(long long)) != cudaSuccess) g_attn_trace = nullptr;
+      else cudaMemset(g_attn_trace, 0, 1024 * sizeof(long long));
+    }
+  }
   if (const char* e = getenv("AF2_X_EVICT_LAST")) g_x_evict_last = atoi(e) != 0;
   if (const char* e = getenv("AF2_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("AF2_PROJ_TRACE")) {

@@ -55,6 +55,7 @@ struct AttnParams {
   __nv_bfloat16* out;         // [token, heads*DH]
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
+  long long* trace;           // debug (AF2_ATTN_TRACE=1): clock64 stamps of CTA 0, 8 per key block, see tools/attn_trace.py
   int l2_prefetch;            // 1: the K producer prefetches K / V / Q / gate boxes ATTN_PF_DIST key blocks ahead into L2 (AF2_ATTN_L2PF)
 };
 
@@ -221,6 +222,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
+  // debug timeline: slot g * 8 + k of CTA 0 (k: 0/1 S issue begin/end, 2/3 P V issue begin/end [MMA warp], 4 S acquired,
+  // 5 P published [softmax warp 2], 6 K landed is implied by 0; 7 item handed to the epilogue)
+  auto stamp = [&](int g, int k) {
+    if (p.trace != nullptr && blockIdx.x == 0 && g < 120) p.trace[g * 8 + k] = clock64();
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -325,6 +331,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       mbar_wait(&k_full[kst], (g / nst) & 1);
       tc_fence_after();
+      if (lane == 0) stamp(g, 0);
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF + (it & 1) * L::Q_BYTES);
         const uint32_t sk = smem_u32(smem + L::STAGE_OFF + kst * stage_stride);
@@ -356,6 +363,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       __syncwarp();
+      if (lane == 0) stamp(g, 1);
     };
     // can S(g) be issued without blocking?  (Q / bias of a new item and the K/V stage have landed; the S buffer itself is
     // free by construction: S(g) is issued after P V(g-2), and the tensor core executes in issue order)
@@ -379,6 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int it = g / nkv, j = g - it * nkv;
       if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
       tc_fence_after();
+      if (lane == 0) stamp(g, 2);
       if (elect_one()) {
         const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
 #pragma unroll
@@ -391,6 +400,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (j == nkv - 1) umma_commit(&o_full[it & 1]);
       }
       __syncwarp();
+      if (lane == 0) stamp(g, 3);
       if (!s_issued) issue_s(g + 1);
     }
   } else if (warp == ATTN_W_KEYMASK) {
@@ -507,6 +517,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j == 0) q_valid = qvbuf[(it & 1) * 128 + r] != 0;
       mbar_wait(&s_full[st], (g >> 1) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) stamp(g, 4);
 
       // logits (log2 domain) = S (pair bias included by the tensor core) + keyterm
       float s[KPT];
@@ -608,6 +619,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0) stamp(g, 5);
       if (lane == 0) mbar_arrive(&p_full[st]);
     }
     }  // work items

@@ -38,6 +38,8 @@ void af2_set_proj_mode(int ctas);
 /* debug aid: with AF2_PROJ_TRACE=1 in the environment the fused projection kernel records clock64 stamps of one CTA
  * (MMA issue, epilogue and producer progress per tile); this copies the 2048 stamps of the last launch to `out` */
 int af2_debug_proj_trace(long long* out);
+/* same for the attention kernel (AF2_ATTN_TRACE=1): 8 stamps per key block of CTA 0 (tools/attn_trace.py), 1024 entries */
+int af2_debug_attn_trace(long long* out);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 unsigned long long af2_launch_count(void);
