@@ -470,6 +470,7 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
+int g_attn_headmajor = 0;  // EXPERIMENT: attention reads a head-major copy of q|k|v (AF2_ATTN_HEADMAJOR=1)
 long long* g_attn_trace = nullptr;   // device buffer of 1024 stamps when AF2_ATTN_TRACE=1 (debug only)
 int g_attn_l2pf = 0;      // 1: attention K producer prefetches upcoming K / V / Q / gate boxes into L2 (AF2_ATTN_L2PF)
 int g_attn_group = 1;     // 1: attention CTAs grouped per (h, b') unit for 2..8 query blocks (AF2_ATTN_GROUP=0: n > 256 ungrouped)
@@ -543,21 +544,31 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 // qkv: bf16 [tokens, 3I] (q | k | v), token(b', i) = b' * tok_sb + i * tok_si
 int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nbatch, long long tok_sb, long long tok_si,
                      const __nv_bfloat16* bias, int npad, const uint8_t* mask, const __nv_bfloat16* gate,
-                     __nv_bfloat16* out, cudaStream_t s) {
+                     __nv_bfloat16* out, cudaStream_t s, const __nv_bfloat16* qkv_hm = nullptr, long long hm_tokens = 0) {
   const long long I = (long long)heads * dh;
   const long long ld = 3 * I;
   CUtensorMap tq, tk, tv, tb, tg, to;
   unsigned long long dims[4] = {(unsigned long long)dh, (unsigned long long)n, (unsigned long long)heads, (unsigned long long)nbatch};
   unsigned long long str[3] = {(unsigned long long)(tok_si * ld * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * ld * 2)};
+  if (qkv_hm) {   // head-major q|k|v [3H][hm_tokens][dh] (experiment AF2_ATTN_HEADMAJOR)
+    str[0] = (unsigned long long)(tok_si * dh * 2); str[1] = (unsigned long long)(hm_tokens * dh * 2); str[2] = (unsigned long long)(tok_sb * dh * 2);
+  }
   unsigned box[4] = {(unsigned)dh, 128, 1, 1};
   const CUtensorMapSwizzle swz = (dh == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   // A box row is ONE head's slice of a token (dh * 2 bytes); the bytes next to it belong to other heads, which other CTAs
   // read at other times, so the L2 fill granularity must not exceed the row (256B promotion doubled the DRAM reads).
   const CUtensorMapL2promotion promo = (dh == 64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz, bf, promo));
-  AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz, bf, promo));
-  AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz, bf, promo));
+  if (qkv_hm) {
+    const long long part = (long long)heads * hm_tokens * dh;
+    AF2_TRY(make_tmap(&tq, qkv_hm, 4, dims, str, box, swz, bf, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    AF2_TRY(make_tmap(&tk, qkv_hm + part, 4, dims, str, box, swz, bf, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    AF2_TRY(make_tmap(&tv, qkv_hm + 2 * part, 4, dims, str, box, swz, bf, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  } else {
+    AF2_TRY(make_tmap(&tq, qkv, 4, dims, str, box, swz, bf, promo));
+    AF2_TRY(make_tmap(&tk, qkv + I, 4, dims, str, box, swz, bf, promo));
+    AF2_TRY(make_tmap(&tv, qkv + 2 * I, 4, dims, str, box, swz, bf, promo));
+  }
   unsigned long long gstr[3] = {(unsigned long long)(tok_si * I * 2), (unsigned long long)(dh * 2), (unsigned long long)(tok_sb * I * 2)};
   AF2_TRY(make_tmap(&tg, gate, 4, dims, gstr, box, swz, bf, promo));
   unsigned obox[4] = {(unsigned)dh, 32, 1, 1};            // the output leaves per 32-row quarter of a query block
@@ -684,6 +695,7 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_GATHER_FUSED")) g_gather_fused = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_GROUP")) g_attn_group = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_L2PF")) g_attn_l2pf = atoi(e) != 0;
+  if (const char* e = getenv("AF2_ATTN_HEADMAJOR")) g_attn_headmajor = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_TRACE")) {
     if (atoi(e) != 0 && !g_attn_trace) {
       if (cudaMalloc(&g_attn_trace, 1024 * sizeof(long long)) != cudaSuccess) g_attn_trace = nullptr;
@@ -754,7 +766,7 @@ long long af2_axial_attention_workspace(int B, int h, int wdim, int d, int heads
   const long long T = (long long)B * h * wdim, I = (long long)heads * dim_head;
   const int n = row_attn ? wdim : h;
   const long long npad = align_up(n, 8);
-  return align_up(T * d * 2, 256) + align_up(T * 3 * I * 2, 256) + 2 * align_up(T * I * 2, 256) +
+  return align_up(T * d * 2, 256) + 2 * align_up(T * 3 * I * 2, 256) + 2 * align_up(T * I * 2, 256) +
          align_up((long long)B * heads * n * npad * 2, 256) + 1024;
 }
 
@@ -778,6 +790,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   __nv_bfloat16* gate = ar.take<__nv_bfloat16>(T * I);
   __nv_bfloat16* og = ar.take<__nv_bfloat16>(T * I);
   __nv_bfloat16* bias = ar.take<__nv_bfloat16>((long long)B * heads * n * npad);
+  __nv_bfloat16* qkv_hm = ar.take<__nv_bfloat16>(T * 3 * I);
   if (!ar.ok) return fail(AF2_ERR_WORKSPACE, "axial_attention: workspace too small");
   if (pre_bias) bias = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(pre_bias));   // [B][H][n][npad], zero padded
 
@@ -844,9 +857,17 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
       tie_queries_kernel<__nv_bfloat16><<<ew_grid((long long)n * I), 256, 0, s>>>(qkv + t0 * 3 * I, 3 * I, (int)I, n, nb, tok_sb, tok_si);
       CUDA_OK(cudaGetLastError());
     }
+    const long long Tb = (long long)h * wdim;
+    if (g_attn_headmajor && dim_head % 8 == 0) {
+      ProfScope ps(s, KC_MISC, 0.0, 0.0);
+      qkv_to_headmajor_kernel<<<ew_grid(Tb * 3 * I / 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(qkv + t0 * 3 * I),
+                                                                        reinterpret_cast<uint4*>(qkv_hm + t0 * 3 * I), Tb, (int)(3 * I), dim_head);
+      CUDA_OK(cudaGetLastError());
+    }
     AF2_TRY(launch_attention(qkv + t0 * 3 * I, heads, dim_head, n, nb, tok_sb, tok_si,
                              has_bias ? bias + (long long)b * heads * n * npad : nullptr, npad,
-                             mask ? mask + t0 : nullptr, gate + t0 * I, og + t0 * I, s));
+                             mask ? mask + t0 : nullptr, gate + t0 * I, og + t0 * I, s,
+                             (g_attn_headmajor && dim_head % 8 == 0) ? qkv_hm + t0 * 3 * I : nullptr, Tb));
   }
   // 4. to_out + bias + residual
   GemmCall co = linear_call(og, I, w->w_out, I, (int)T, d, (int)I);

@@ -223,7 +223,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();
   // debug timeline: slot g * 8 + k of CTA 0 (k: 0/1 S issue begin/end, 2/3 P V issue begin/end [MMA warp], 4 S acquired,
-  // 5 P published [softmax warp 2], 6 K landed is implied by 0; 7 item handed to the epilogue)
+  // 5 P published [softmax warp 2], 6 K load issued [producer], 7 MMA warp free to issue S of this block)
   auto stamp = [&](int g, int k) {
     if (p.trace != nullptr && blockIdx.x == 0 && g < 120) p.trace[g * 8 + k] = clock64();
   };
@@ -276,6 +276,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           prefetch_block(g + ATTN_PF_DIST);
           // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
           mbar_wait(&k_empty[kst], ((g / nst) & 1) ^ 1);
+          stamp(g, 6);
           uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
           mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
           tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
@@ -380,6 +381,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = g & 1;
       // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
       bool s_issued = g + 1 >= total_blocks;
+      if (lane == 0) stamp(g + 1, 7);                    // the MMA warp starts looking for S(g + 1)'s operands
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
