@@ -56,6 +56,7 @@ struct AttnParams {
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
   long long* trace;           // debug (AF2_ATTN_TRACE=1): clock64 stamps of CTA 0, 8 per key block, see tools/attn_trace.py
+  int k_stages3;              // 1: three K stages in resident-bias mode (AF2_ATTN_K3, default on)
   int l2_prefetch;            // 1: the K producer prefetches K / V / Q / gate boxes ATTN_PF_DIST key blocks ahead into L2 (AF2_ATTN_L2PF)
 };
 
@@ -169,8 +170,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   };
   auto combo_of = [&](int it) { return (item0 + it) / p.nbatch; };       // changes with (h, query block): selects the bias tiles
   const bool resident = p.has_bias && nkv <= 2;
-  const int nst = p.has_bias ? 2 : 4;                                    // K/V pipeline depth
+  const int nst = p.has_bias ? 2 : 4;                                    // V pipeline depth (and K's, except below)
+  // Resident-bias mode: THREE K stages.  The timeline (AF2_ATTN_TRACE, profiles/r02m_attn_trace_*.txt) shows a K box landing
+  // ~5400 cycles after its load is issued in steady state (1600 cold), and the load of block g + 2 can only be issued
+  // when block g's S retires: with two stages the block period was (5400 + 900) / 2 -- the whole kernel ran at the pace of
+  // that round trip.  The third stage lives in what used to be the second gate-tile slot (the gate tile is single buffered
+  // in this mode: it is needed one item later, by the epilogue).  V stays at two stages: it is needed a softmax later.
+  const bool k3 = resident && p.k_stages3 != 0;
+  const int nstk = k3 ? 3 : nst;                                         // K pipeline depth
   const int stage_stride = (p.has_bias && !resident) ? L::STAGE_BYTES : L::KV_BYTES;
+  auto k_off = [&](int kst) { return (k3 && kst == 2) ? (L::G_OFF + L::Q_BYTES) : (L::STAGE_OFF + kst * stage_stride); };
+  auto g_slot = [&](int it) { return k3 ? 0 : (it & 1); };
+  auto g_phase = [&](int it) { return static_cast<uint32_t>(k3 ? (it & 1) : ((it >> 1) & 1)); };
   const int bias_res_off = L::STAGE_OFF + 2 * L::KV_BYTES;               // resident tiles: + j * BIAS_BYTES
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0, O_COL = 256;
@@ -272,12 +283,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool stream_bias = p.has_bias && !resident;
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
-          const int kst = g % nst;
+          const int kst = g % nstk;
           prefetch_block(g + ATTN_PF_DIST);
           // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
-          mbar_wait(&k_empty[kst], ((g / nst) & 1) ^ 1);
+          mbar_wait(&k_empty[kst], ((g / nstk) & 1) ^ 1);
           stamp(g, 6);
-          uint8_t* sk = smem + L::STAGE_OFF + kst * stage_stride;
+          uint8_t* sk = smem + k_off(kst);
           mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
           tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
           if (stream_bias) {
@@ -306,10 +317,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
           tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
         }
-        const int gs = it & 1;
-        mbar_wait(&g_empty[gs], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
-        tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
+        if (!k3) {                                   // (k3: the epilogue warps read the gate straight from global memory)
+          const int gs = g_slot(it);
+          mbar_wait(&g_empty[gs], g_phase(it) ^ 1);
+          mbar_arrive_expect_tx(&g_full[gs], L::Q_BYTES);
+          tma_load_4d(smem + L::G_OFF + gs * L::Q_BYTES, &tmG, &g_full[gs], 0, qb * 128, h, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -321,7 +334,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int prev_combo = -1, nc = 0;
     auto issue_s = [&](int g) {
       const int it = g / nkv, j = g - it * nkv;
-      const int st = g & 1, kst = g % nst;
+      const int st = g & 1, kst = g % nstk;
       if (j == 0) {
         mbar_wait(&q_full[it & 1], (it >> 1) & 1);
         if (resident && combo_of(it) != prev_combo) {     // this CTA's range entered the next (h, query block): new bias tiles
@@ -330,12 +343,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ++nc;
         }
       }
-      mbar_wait(&k_full[kst], (g / nst) & 1);
+      mbar_wait(&k_full[kst], (g / nstk) & 1);
       tc_fence_after();
       if (lane == 0) stamp(g, 0);
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF + (it & 1) * L::Q_BYTES);
-        const uint32_t sk = smem_u32(smem + L::STAGE_OFF + kst * stage_stride);
+        const uint32_t sk = smem_u32(smem + k_off(kst));
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
           const uint64_t ad = umma_smem_desc(sq + k * 32, 16, SBO, SWZ);
@@ -374,7 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (!mbar_test(&q_full[it & 1], (it >> 1) & 1)) return false;
         if (resident && combo_of(it) != prev_combo && !mbar_test(bias_full, nc & 1)) return false;
       }
-      return mbar_test(&k_full[g % nst], (g / nst) & 1);
+      return mbar_test(&k_full[g % nstk], (g / nstk) & 1);
     };
     if (total_blocks > 0) issue_s(0);
     for (int g = 0; g < total_blocks; ++g) {
@@ -450,14 +463,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int qb, h, b;
       decode(it, qb, h, b);
       const int slot = it & 1;
+      // k3 mode (three K stages; the second gate slot holds K stage 2): the gate row of this thread's query comes straight
+      // from global memory into registers BEFORE the wait for the item's O -- the load latency hides behind that wait and the
+      // remaining gate slot is only the staging tile of the TMA store.  A single-buffered TMA-loaded gate tile would put the
+      // ~5000-cycle load behind the previous item's store and throttle the kernel to the old pace.
+      uint4 greg[DH / 8];
+      if (k3) {
+        const int qi = qb * 128 + r;
+        const uint4* grow = reinterpret_cast<const uint4*>(p.gate + (static_cast<long long>(b) * p.tok_sb + static_cast<long long>(qi) * p.tok_si) * p.ld_gate + h * DH);
+#pragma unroll
+        for (int i = 0; i < DH / 8; ++i) greg[i] = (qi < p.n) ? __ldg(grow + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&o_full[slot], (it >> 1) & 1);
       tc_fence_after();
       float lsum = 0.f;
 #pragma unroll
       for (int i = 0; i < ATTN_NSPLIT; ++i) lsum += lbuf[(slot * ATTN_NSPLIT + i) * 128 + r];
       const float inv_l = 1.0f / lsum;
-      mbar_wait(&g_full[slot], (it >> 1) & 1);
-      uint8_t* gt = smem + L::G_OFF + slot * L::Q_BYTES;
+      const int gsl = g_slot(it);
+      if (!k3) mbar_wait(&g_full[gsl], g_phase(it));
+      uint8_t* gt = smem + L::G_OFF + gsl * L::Q_BYTES;
 #pragma unroll
       for (int half = 0; half < DH / 32; ++half) {
         uint32_t o[32];
@@ -473,7 +498,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // gate tile rows are DH*2 bytes with the TMA swizzle of Q (128B for DH = 64, 64B for DH = 32); the gated output
           // replaces the gate values it was computed from, in the same (swizzled) place
           const uint32_t goff = (DH == 64) ? swz128_off(r, half * 4 + i) : (r * 64u + ((static_cast<uint32_t>(i) ^ ((r >> 1) & 3u)) << 4));
-          const uint4 gq = *reinterpret_cast<const uint4*>(gt + goff);
+          const uint4 gq = k3 ? greg[half * 4 + i] : *reinterpret_cast<const uint4*>(gt + goff);
           const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
           uint32_t ow[4];
 #pragma unroll
@@ -492,7 +517,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
         tma_store_commit();
         tma_store_wait_read<0>();                        // the store has drained the tile: hand the slot back to the producer
-        mbar_arrive(&g_empty[slot]);
+        if (!k3) mbar_arrive(&g_empty[gsl]);
       }
       __syncwarp();
     }
