@@ -56,6 +56,7 @@ struct AttnParams {
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
   long long* trace;           // debug (AF2_ATTN_TRACE=1): clock64 stamps of CTA 0, 8 per key block, see tools/attn_trace.py
+  int dbg_skip;               // DEBUG (AF2_ATTN_SKIP): bit 0 skip the V loads, bit 1 the K loads, bit 2 the Q loads, bit 3 the output stores (results wrong; timing experiments only)
   int k_stages3;              // 1: three K stages in resident-bias mode (AF2_ATTN_K3, default on)
   int l2_prefetch;            // 1: the K producer prefetches K / V / Q / gate boxes ATTN_PF_DIST key blocks ahead into L2 (AF2_ATTN_L2PF)
 };
@@ -236,7 +237,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // debug timeline: slot g * 8 + k of CTA 0 (k: 0/1 S issue begin/end, 2/3 P V issue begin/end [MMA warp], 4 S acquired,
   // 5 P published [softmax warp 2], 6 K load issued [producer], 7 MMA warp free to issue S of this block)
   auto stamp = [&](int g, int k) {
-    if (p.trace != nullptr && blockIdx.x == 0 && g < 120) p.trace[g * 8 + k] = clock64();
+    if (p.trace != nullptr && blockIdx.x == 0 && g < 64) p.trace[g * 16 + k] = clock64();
   };
 
   if (warp == 0) {
@@ -276,8 +277,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ++nc;
         }
         mbar_wait(&q_empty[gs], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[gs], L::Q_BYTES);
-        tma_load_4d(smem + L::Q_OFF + gs * L::Q_BYTES, &tmQ, &q_full[gs], 0, qb * 128, h, b);
+        if (p.dbg_skip & 4) mbar_arrive(&q_full[gs]);
+        else {
+          mbar_arrive_expect_tx(&q_full[gs], L::Q_BYTES);
+          tma_load_4d(smem + L::Q_OFF + gs * L::Q_BYTES, &tmQ, &q_full[gs], 0, qb * 128, h, b);
+        }
         // (the gate tile of the item is loaded by the V producer warp: its slot is handed back by the epilogue of item
         // it - 2, and waiting for that HERE delayed the K loads of the next item -- see the note there)
         const bool stream_bias = p.has_bias && !resident;
@@ -289,6 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&k_empty[kst], ((g / nstk) & 1) ^ 1);
           stamp(g, 6);
           uint8_t* sk = smem + k_off(kst);
+          if ((p.dbg_skip & 2) && !stream_bias) { mbar_arrive(&k_full[kst]); continue; }
           mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
           tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
           if (stream_bias) {
@@ -314,6 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int g = it * nkv + j;
           const int kst = g % nst;
           mbar_wait(&v_empty[kst], ((g / nst) & 1) ^ 1);
+          if (p.dbg_skip & 1) { mbar_arrive(&v_full[kst]); continue; }
           mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
           tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
         }
@@ -343,7 +349,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ++nc;
         }
       }
+      if (lane == 0) stamp(g, 8);                       // entered issue_s (after the Q / bias waits of a first block)
       mbar_wait(&k_full[kst], (g / nstk) & 1);
+      if (lane == 0) stamp(g, 9);                       // K landed
       tc_fence_after();
       if (lane == 0) stamp(g, 0);
       if (elect_one()) {
@@ -395,7 +403,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
       bool s_issued = g + 1 >= total_blocks;
       if (lane == 0) stamp(g + 1, 7);                    // the MMA warp starts looking for S(g + 1)'s operands
+      bool first = true;
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
+        if (first && lane == 0) stamp(g + 1, 10);       // first p_full probe came back (not ready)
+        first = false;
         if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
       }
       mbar_wait(&v_full[g % nst], (g / nst) & 1);
@@ -514,7 +525,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         // this warp's 32 rows of the tile; rows beyond n are clipped by the tensor map
-        tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
+        if (!(p.dbg_skip & 8)) tma_store_4d(&tmO, gt + q * 32 * ROWB, 0, qb * 128 + q * 32, h, b);
         tma_store_commit();
         tma_store_wait_read<0>();                        // the store has drained the tile: hand the slot back to the producer
         if (!k3) mbar_arrive(&g_empty[gsl]);

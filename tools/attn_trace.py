@@ -30,11 +30,11 @@ t = list(buf)
 t0 = min(v for v in t if v > 0)
 print(f"# N={N}: per key block g of CTA 0 (cycles since the first stamp): S_issue[begin end]  PV_issue[begin end]  S_acquired  P_published")
 prev = None
-for g in range(120):
-    r = t[g * 8: g * 8 + 8]
+for g in range(64):
+    r = t[g * 16: g * 16 + 16]
     if not any(r[:6]):
         break
     rel = [(v - t0) if v > 0 else -1 for v in r]
     period = "" if prev is None or rel[5] < 0 else f"  period {rel[5] - prev}"
     prev = rel[5] if rel[5] >= 0 else prev
-    print(f"g={g:3d}  S[{rel[0]:7d} {rel[1]:7d}]  PV[{rel[2]:7d} {rel[3]:7d}]  S_acq {rel[4]:7d}  P_pub {rel[5]:7d}  softmax {rel[5] - rel[4]:5d}  K_issue {rel[6]:7d} (S waits K: {rel[0] - rel[6]:5d})  MMA_free {rel[7]:7d}{period}")
+    print(f"g={g:3d}  S[{rel[0]:7d} {rel[1]:7d}]  PV[{rel[2]:7d} {rel[3]:7d}]  S_acq {rel[4]:7d}  P_pub {rel[5]:7d}  softmax {rel[5] - rel[4]:5d}  K_issue {rel[6]:7d}  MMA_free {rel[7]:7d} probe {rel[10]:7d} issue_s {rel[8]:7d} K_ok {rel[9]:7d}{period}")
