@@ -470,6 +470,7 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
+int g_attn_ident_tmem = 1;  // 1: bias-MMA identity operand in tensor memory (AF2_ATTN_IDENT_TMEM=0: shared-memory strip)
 int g_attn_skip = 0;       // DEBUG timing experiments (AF2_ATTN_SKIP bitmask, results wrong)
 int g_attn_k3 = 0;         // 1: three K stages in the attention kernel's resident-bias mode (AF2_ATTN_K3)
 int g_attn_headmajor = 0;  // EXPERIMENT: attention reads a head-major copy of q|k|v (AF2_ATTN_HEADMAJOR=1)
@@ -591,6 +592,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.l2_prefetch = g_attn_l2pf;
   p.k_stages3 = g_attn_k3;
   p.dbg_skip = g_attn_skip;
+  p.ident_tmem = g_attn_ident_tmem;
   p.trace = g_attn_trace;
   if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
   if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
@@ -702,6 +704,7 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_ATTN_HEADMAJOR")) g_attn_headmajor = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_K3")) g_attn_k3 = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_SKIP")) g_attn_skip = atoi(e);
+  if (const char* e = getenv("AF2_ATTN_IDENT_TMEM")) g_attn_ident_tmem = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_TRACE")) {
     if (atoi(e) != 0 && !g_attn_trace) {
       if (cudaMalloc(&g_attn_trace, 1024 * sizeof(long long)) != cudaSuccess) g_attn_trace = nullptr;

@@ -56,6 +56,7 @@ struct AttnParams {
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
   long long* trace;           // debug (AF2_ATTN_TRACE=1): clock64 stamps of CTA 0, 8 per key block, see tools/attn_trace.py
+  int ident_tmem;             // 1: the identity operand of the bias MMA lives in tensor memory (AF2_ATTN_IDENT_TMEM)
   int dbg_skip;               // DEBUG (AF2_ATTN_SKIP): bit 0 skip the V loads, bit 1 the K loads, bit 2 the Q loads, bit 3 the output stores (results wrong; timing experiments only)
   int k_stages3;              // 1: three K stages in resident-bias mode (AF2_ATTN_K3, default on)
   int l2_prefetch;            // 1: the K producer prefetches K / V / Q / gate boxes ATTN_PF_DIST key blocks ahead into L2 (AF2_ATTN_L2PF)
@@ -232,6 +233,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Identity operand of the bias MMA in TENSOR memory (p.ident_tmem): A[r][k] = (r == k) as packed bf16 pairs in 64 columns
+  // (column k / 2, low half = even k), written once per CTA.  With the identity read from shared memory (32-byte rows,
+  // SW32 strip) the eight K = 16 bias steps took ~1000 cycles per key block -- twice their tensor-pipe time, and the whole S
+  // issue (1300 cycles, AF2_ATTN_TRACE) sits on the kernel's critical path between two softmax phases.
+  constexpr uint32_t IDENT_COL = 384;
+  if (p.has_bias && p.ident_tmem && warp >= ATTN_W_EPI) {
+    const uint32_t r = (warp & 3) * 32 + lane;
+    uint32_t v[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = (static_cast<uint32_t>(half * 32 + c) == (r >> 1)) ? ((r & 1) ? 0x3f800000u : 0x00003f80u) : 0u;
+      tmem_st32(tmem_base + IDENT_COL + half * 32 + (static_cast<uint32_t>((warp & 3) * 32) << 16), v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  if (p.has_bias && p.ident_tmem) {
+    __syncthreads();
+    tc_fence_after();
+  }
   pdl_launch_dependents();
   pdl_wait();
   // debug timeline: slot g * 8 + k of CTA 0 (k: 0/1 S issue begin/end, 2/3 P V issue begin/end [MMA warp], 4 S acquired,
@@ -369,12 +391,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t sbz = resident ? smem_u32(smem + bias_res_off + j * L::BIAS_BYTES) : sk + L::KV_BYTES;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // A: identity columns 16k .. 16k+15 = the diagonal strip entered (14 - 2k) row groups in (see AttnSmem)
-            const uint64_t ad = umma_smem_desc(si + (14 - 2 * k) * 256, 16, 256, SWZ_32);
             // B: bias rows (the K index) 16k .. 16k+15 with the keys contiguous (MN-major): 8-row atoms 1024 B apart,
             // the two 64-key boxes 16 KB apart
             const uint64_t bd = umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
-            umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_b, 1u);
+            if (p.ident_tmem) {
+              // A: identity columns 16k .. 16k+15 from tensor memory (8 packed columns)
+              umma_bf16_ts(tmem_base + S_COL + st * 128, tmem_base + IDENT_COL + k * 8, bd, idesc_b, 1u);
+            } else {
+              // A: identity columns 16k .. 16k+15 = the diagonal strip entered (14 - 2k) row groups in (see AttnSmem)
+              const uint64_t ad = umma_smem_desc(si + (14 - 2 * k) * 256, 16, 256, SWZ_32);
+              umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_b, 1u);
+            }
           }
         }
         umma_commit(&s_full[st]);
