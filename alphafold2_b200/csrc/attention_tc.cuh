@@ -281,8 +281,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_prefetch_4d(&tmG, 0, qb2 * 128, h2, b2);
         }
       };
-      for (int g = 0; g < ATTN_PF_DIST; ++g) prefetch_block(g);
+      if (p.l2_prefetch) for (int g = 0; g < ATTN_PF_DIST; ++g) prefetch_block(g);
       int prev_combo = -1, nc = 0;
+      int kst = 0;                                       // K ring stage / phase of the next block, kept incrementally
+      uint32_t kph = 0;
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
         decode(it, qb, h, b);
@@ -309,19 +311,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool stream_bias = p.has_bias && !resident;
         for (int j = 0; j < nkv; ++j) {
           const int g = it * nkv + j;
-          const int kst = g % nstk;
-          prefetch_block(g + ATTN_PF_DIST);
+          if (p.l2_prefetch) prefetch_block(g + ATTN_PF_DIST);
           // K is dead as soon as the block's S MMAs retire -- a whole softmax earlier than V -- so its stage refills early
-          mbar_wait(&k_empty[kst], ((g / nstk) & 1) ^ 1);
+          const int ks = kst;
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          if (++kst == nstk) { kst = 0; kph ^= 1; }
           stamp(g, 6);
-          uint8_t* sk = smem + k_off(kst);
-          if ((p.dbg_skip & 2) && !stream_bias) { mbar_arrive(&k_full[kst]); continue; }
-          mbar_arrive_expect_tx(&k_full[kst], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
-          tma_load_4d(sk, &tmK, &k_full[kst], 0, j * 128, h, b);
+          uint8_t* sk = smem + k_off(ks);
+          if ((p.dbg_skip & 2) && !stream_bias) { mbar_arrive(&k_full[ks]); continue; }
+          mbar_arrive_expect_tx(&k_full[ks], L::K_BYTES + (stream_bias ? L::BIAS_BYTES : 0));
+          tma_load_4d(sk, &tmK, &k_full[ks], 0, j * 128, h, b);
           if (stream_bias) {
             uint8_t* sbias = sk + L::KV_BYTES;
-            tma_load_3d(sbias, &tmBias, &k_full[kst], j * 128, qb * 128, h);
-            tma_load_3d(sbias + 16384, &tmBias, &k_full[kst], j * 128 + 64, qb * 128, h);
+            tma_load_3d(sbias, &tmBias, &k_full[ks], j * 128, qb * 128, h);
+            tma_load_3d(sbias + 16384, &tmBias, &k_full[ks], j * 128 + 64, qb * 128, h);
           }
         }
       }
@@ -334,13 +337,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // 31 % of the softmax warps' samples on the s_full wait, block period 3800 cycles for ~1000 cycles of tensor work).
     // Here it follows the item's V loads, where it delays nothing.
     if (lane == 0) {
+      int vst = 0;                                       // V ring stage / phase of the next block, kept incrementally
+      uint32_t vph = 0;
       for (int it = 0; it < my_items; ++it) {
         int qb, h, b;
         decode(it, qb, h, b);
         for (int j = 0; j < nkv; ++j) {
-          const int g = it * nkv + j;
-          const int kst = g % nst;
-          mbar_wait(&v_empty[kst], ((g / nst) & 1) ^ 1);
+          const int kst = vst;
+          mbar_wait(&v_empty[kst], vph ^ 1);
+          if (++vst == nst) { vst = 0; vph ^= 1; }
           if (p.dbg_skip & 1) { mbar_arrive(&v_full[kst]); continue; }
           mbar_arrive_expect_tx(&v_full[kst], L::V_BYTES);
           tma_load_4d(smem + L::STAGE_OFF + kst * stage_stride + L::K_BYTES, &tmV, &v_full[kst], 0, j * 128, h, b);
@@ -359,23 +364,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr uint32_t idesc_b = umma_idesc_bf16(128, 128, 0, 1);   // S += I B: identity K-major, bias tile MN-major
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, P from tensor memory, V MN-major
     const int total_blocks = my_items * nkv;
-    int prev_combo = -1, nc = 0;
-    auto issue_s = [&](int g) {
-      const int it = g / nkv, j = g - it * nkv;
-      const int st = g & 1, kst = g % nstk;
+    // Every index of the two block streams this warp walks (S issue runs one block ahead of P V) is kept INCREMENTALLY:
+    // the first version recomputed it = g / nkv, g % stages, (g / stages) & 1 and the bias-tile combo (item / nbatch) with
+    // run-time divisors on every probe -- ~150 cycles of dependent I2F / MUFU.RCP / F2I chain each, 5-8 of them between
+    // "P V issued" and "S of the next block issued" (AF2_ATTN_TRACE showed ~900 cycles there), on the one warp whose latency
+    // every key block waits for.
+    struct Walk { int g, it, j, kst, kph; };             // block g = key block j of item it; ring stage kst, ring phase kph
+    Walk sw = {0, 0, 0, 0, 0};                           // next block whose S is to be issued (K ring, depth nstk)
+    Walk pw = {0, 0, 0, 0, 0};                           // block whose P V is issued next (V ring, depth nst)
+    auto advance = [&](Walk& w, int depth) {
+      ++w.g;
+      if (++w.j == nkv) { w.j = 0; ++w.it; }
+      if (++w.kst == depth) { w.kst = 0; w.kph ^= 1; }
+    };
+    // bias-tile combo (h, query block) of the S stream's item: it changes when (item0 + it) crosses a multiple of nbatch
+    int combo_rem = item0 % p.nbatch;                    // (item0 + sw.it) % nbatch  (one division per kernel)
+    bool combo_new = true;                               // the item sw.it is the first of its combo (or the CTA's first item)
+    int nc = 0;
+    auto issue_s = [&]() {
+      const int g = sw.g, it = sw.it, j = sw.j, kst = sw.kst;
+      const int st = g & 1;
       if (j == 0) {
         mbar_wait(&q_full[it & 1], (it >> 1) & 1);
-        if (resident && combo_of(it) != prev_combo) {     // this CTA's range entered the next (h, query block): new bias tiles
-          prev_combo = combo_of(it);
+        if (resident && combo_new) {                       // this CTA's range entered the next (h, query block): new bias tiles
           mbar_wait(bias_full, nc & 1);
           ++nc;
         }
       }
       if (lane == 0) stamp(g, 8);                       // entered issue_s (after the Q / bias waits of a first block)
-      mbar_wait(&k_full[kst], (g / nstk) & 1);
+      mbar_wait(&k_full[kst], sw.kph);
       if (lane == 0) stamp(g, 9);                       // K landed
       tc_fence_after();
       if (lane == 0) stamp(g, 0);
+      const bool last_of_item = (j == nkv - 1);
+      const bool last_of_combo = last_of_item && (it + 1 == my_items || combo_rem == p.nbatch - 1);
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + L::Q_OFF + (it & 1) * L::Q_BYTES);
         const uint32_t sk = smem_u32(smem + k_off(kst));
@@ -406,25 +428,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[kst]);
-        if (j == nkv - 1) {
+        if (last_of_item) {
           umma_commit(&q_empty[it & 1]);                   // Q slot reusable once the item's last QK^T retires
-          if (resident && (it + 1 == my_items || combo_of(it + 1) != prev_combo)) umma_commit(bias_empty);
+          if (resident && last_of_combo) umma_commit(bias_empty);
         }
       }
       __syncwarp();
       if (lane == 0) stamp(g, 1);
-    };
-    // can S(g) be issued without blocking?  (Q / bias of a new item and the K/V stage have landed; the S buffer itself is
-    // free by construction: S(g) is issued after P V(g-2), and the tensor core executes in issue order)
-    auto s_ready = [&](int g) {
-      const int it = g / nkv, j = g - it * nkv;
-      if (j == 0) {
-        if (!mbar_test(&q_full[it & 1], (it >> 1) & 1)) return false;
-        if (resident && combo_of(it) != prev_combo && !mbar_test(bias_full, nc & 1)) return false;
+      if (last_of_item) {                                  // the S stream moves on to the next item
+        combo_new = (combo_rem == p.nbatch - 1);
+        combo_rem = combo_new ? 0 : combo_rem + 1;
+      } else {
+        combo_new = false;
       }
-      return mbar_test(&k_full[g % nstk], (g / nstk) & 1);
+      advance(sw, nstk);
     };
-    if (total_blocks > 0) issue_s(0);
+    // can S of the next block be issued without blocking?  (Q / bias of a new item and the K stage have landed; the S buffer
+    // itself is free by construction: S(g) is issued after P V(g-2), and the tensor core executes in issue order)
+    auto s_ready = [&]() {
+      if (sw.j == 0) {
+        if (!mbar_test(&q_full[sw.it & 1], (sw.it >> 1) & 1)) return false;
+        if (resident && combo_new && !mbar_test(bias_full, nc & 1)) return false;
+      }
+      return mbar_test(&k_full[sw.kst], sw.kph);
+    };
+    if (total_blocks > 0) issue_s();
     for (int g = 0; g < total_blocks; ++g) {
       const int st = g & 1;
       // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
@@ -434,27 +462,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (first && lane == 0) stamp(g + 1, 10);       // first p_full probe came back (not ready)
         first = false;
-        if (!s_issued && s_ready(g + 1)) { issue_s(g + 1); s_issued = true; }
+        if (!s_issued && s_ready()) { issue_s(); s_issued = true; }
       }
-      mbar_wait(&v_full[g % nst], (g / nst) & 1);
-      const int it = g / nkv, j = g - it * nkv;
+      mbar_wait(&v_full[pw.kst], pw.kph);
+      const int it = pw.it, j = pw.j;
       if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
       tc_fence_after();
       if (lane == 0) stamp(g, 2);
       if (elect_one()) {
-        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + (g % nst) * stage_stride + L::K_BYTES);
+        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + pw.kst * stage_stride + L::K_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A = P [128 rows x 16 keys] = 8 packed columns of the S / P buffer; B = V [key][dh], MN-major: 16 keys = 2 atoms
           const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
           umma_bf16_ts(tmem_base + O_COL + (it & 1) * 64, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (j != 0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[g % nst]);
+        umma_commit(&v_empty[pw.kst]);
         if (j == nkv - 1) umma_commit(&o_full[it & 1]);
       }
       __syncwarp();
       if (lane == 0) stamp(g, 3);
-      if (!s_issued) issue_s(g + 1);
+      advance(pw, nst);
+      if (!s_issued) issue_s();
     }
   } else if (warp == ATTN_W_KEYMASK) {
     // ================================ key-mask warp ================================
