@@ -381,18 +381,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int combo_rem = item0 % p.nbatch;                    // (item0 + sw.it) % nbatch  (one division per kernel)
     bool combo_new = true;                               // the item sw.it is the first of its combo (or the CTA's first item)
     int nc = 0;
-    auto issue_s = [&]() {
+    // `probed`: s_ready() has just seen every operand barrier of this block complete (a successful test_wait acquires like a
+    // wait), so the waits -- ~100 cycles of SYNCS round trip each on this latency-bound warp -- are skipped
+    auto issue_s = [&](bool probed) {
       const int g = sw.g, it = sw.it, j = sw.j, kst = sw.kst;
       const int st = g & 1;
       if (j == 0) {
-        mbar_wait(&q_full[it & 1], (it >> 1) & 1);
+        if (!probed) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
         if (resident && combo_new) {                       // this CTA's range entered the next (h, query block): new bias tiles
-          mbar_wait(bias_full, nc & 1);
+          if (!probed) mbar_wait(bias_full, nc & 1);
           ++nc;
         }
       }
       if (lane == 0) stamp(g, 8);                       // entered issue_s (after the Q / bias waits of a first block)
-      mbar_wait(&k_full[kst], sw.kph);
+      if (!probed) mbar_wait(&k_full[kst], sw.kph);
       if (lane == 0) stamp(g, 9);                       // K landed
       tc_fence_after();
       if (lane == 0) stamp(g, 0);
@@ -452,17 +454,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       return mbar_test(&k_full[sw.kst], sw.kph);
     };
-    if (total_blocks > 0) issue_s();
+    if (total_blocks > 0) issue_s(false);
     for (int g = 0; g < total_blocks; ++g) {
       const int st = g & 1;
-      // S(g+1) goes out as early as its operands allow, but P V(g) never queues behind a K/V load that is still in flight
+      // S(g+1) goes out as early as its operands allow (it is tried BEFORE the first look at P(g): in steady state P(g) is
+      // still a softmax away), but P V(g) never queues behind a K/V load that is still in flight
       bool s_issued = g + 1 >= total_blocks;
       if (lane == 0) stamp(g + 1, 7);                    // the MMA warp starts looking for S(g + 1)'s operands
+      if (!s_issued && s_ready()) { issue_s(true); s_issued = true; }
       bool first = true;
       while (!mbar_test(&p_full[st], (g >> 1) & 1)) {
         if (first && lane == 0) stamp(g + 1, 10);       // first p_full probe came back (not ready)
         first = false;
-        if (!s_issued && s_ready()) { issue_s(); s_issued = true; }
+        if (!s_issued && s_ready()) { issue_s(true); s_issued = true; }
       }
       mbar_wait(&v_full[pw.kst], pw.kph);
       const int it = pw.it, j = pw.j;
@@ -483,7 +487,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) stamp(g, 3);
       advance(pw, nst);
-      if (!s_issued) issue_s();
+      if (!s_issued) issue_s(false);
     }
   } else if (warp == ATTN_W_KEYMASK) {
     // ================================ key-mask warp ================================
