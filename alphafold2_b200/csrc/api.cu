@@ -411,11 +411,12 @@ int launch_layernorm(const LnParams& p, cudaStream_t s) {
 // pair bias <x_raw, w_edge> of T tokens (d % 32 == 0, d <= 256, heads <= 8), else the LayerNorm kernel's bias path
 bool pair_bias_fast_ok(int d, int heads) { return d % 32 == 0 && d >= 32 && d <= 256 && heads <= 8; }
 int launch_pair_bias(const float* x, long long T, int d, const float* wb, __nv_bfloat16* bias_out, int heads, long long bias_hs,
-                     int n_inner, int pitch, cudaStream_t s) {
+                     int n_inner, int pitch, cudaStream_t s, int transpose = 0) {
   if (T <= 0) return AF2_OK;
   PairBiasParams p;
   p.x = x; p.T = T; p.d = d; p.wb = wb; p.bias_out = bias_out; p.heads = heads; p.bias_hs = bias_hs; p.n_inner = n_inner; p.pitch = pitch;
   p.x_evict_last = x_hint(T, d);
+  p.transpose = transpose;
   if (T > 0x7fffffffLL) return fail(AF2_ERR_BAD_ARG, "pair_bias: too many tokens");
   const bool mma = (d == 256 || d == 128);
   const long long need = mma ? (T + 127) / 128 : (T + 31) / 32;   // 8 warps x 16 (tensor-core kernel) / 4 tokens per block iteration
@@ -470,6 +471,7 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
+int g_attn_bias_t = 1;      // 1: pair bias stored transposed ([h][key][query]) so the bias MMA's B operand is K-major (AF2_ATTN_BIAS_T)
 int g_attn_ident_tmem = 1;  // 1: bias-MMA identity operand in tensor memory (AF2_ATTN_IDENT_TMEM=0: shared-memory strip)
 int g_attn_skip = 0;       // DEBUG timing experiments (AF2_ATTN_SKIP bitmask, results wrong)
 int g_attn_k3 = 0;         // 1: three K stages in the attention kernel's resident-bias mode (AF2_ATTN_K3)
@@ -547,7 +549,7 @@ int launch_attention_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 // qkv: bf16 [tokens, 3I] (q | k | v), token(b', i) = b' * tok_sb + i * tok_si
 int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nbatch, long long tok_sb, long long tok_si,
                      const __nv_bfloat16* bias, int npad, const uint8_t* mask, const __nv_bfloat16* gate,
-                     __nv_bfloat16* out, cudaStream_t s, const __nv_bfloat16* qkv_hm = nullptr, long long hm_tokens = 0) {
+                     __nv_bfloat16* out, cudaStream_t s, const __nv_bfloat16* qkv_hm = nullptr, long long hm_tokens = 0, int bias_t = 0) {
   const long long I = (long long)heads * dh;
   const long long ld = 3 * I;
   CUtensorMap tq, tk, tv, tb, tg, to;
@@ -593,6 +595,7 @@ int launch_attention(const __nv_bfloat16* qkv, int heads, int dh, int n, int nba
   p.k_stages3 = g_attn_k3;
   p.dbg_skip = g_attn_skip;
   p.ident_tmem = g_attn_ident_tmem;
+  p.bias_t = bias_t;
   p.trace = g_attn_trace;
   if (dh == 64) return launch_attention_inst<64>(tq, tk, tv, tb, tg, to, p, s);
   if (dh == 32) return launch_attention_inst<32>(tq, tk, tv, tb, tg, to, p, s);
@@ -705,6 +708,7 @@ int af2_check_device(void) {
   if (const char* e = getenv("AF2_ATTN_K3")) g_attn_k3 = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_SKIP")) g_attn_skip = atoi(e);
   if (const char* e = getenv("AF2_ATTN_IDENT_TMEM")) g_attn_ident_tmem = atoi(e) != 0;
+  if (const char* e = getenv("AF2_ATTN_BIAS_T")) g_attn_bias_t = atoi(e) != 0;
   if (const char* e = getenv("AF2_ATTN_TRACE")) {
     if (atoi(e) != 0 && !g_attn_trace) {
       if (cudaMalloc(&g_attn_trace, 1024 * sizeof(long long)) != cudaSuccess) g_attn_trace = nullptr;
@@ -809,6 +813,8 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.gamma = w->ln_gamma; lp.beta = w->ln_beta; lp.y = xn; lp.T = T; lp.d = d; lp.eps = 1e-5f;
   const bool fuse_bias = has_bias && !pre_bias && edges == x && B == 1;
+  // transposed bias [h][key][query] (K-major operand of the bias MMA) whenever the dedicated pair-bias kernel produces it
+  const bool bias_t = g_attn_bias_t && has_bias && !pre_bias && pair_bias_fast_ok(d, heads) && !(fuse_bias && !fused_proj);
   // pad key columns are loaded by TMA next to valid ones: keep them finite (zero)
   if (has_bias && !pre_bias && npad != n) CUDA_OK(cudaMemsetAsync(bias, 0, (size_t)B * heads * n * npad * 2, s));
   if (fuse_bias) {
@@ -819,7 +825,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   } else if (fuse_bias) {
     // pair bias only (raw x . w_edge); the LayerNorm itself is fused into the projection
     if (pair_bias_fast_ok(d, heads)) {
-      AF2_TRY(launch_pair_bias(x, T, d, w->w_edge, bias, heads, (long long)n * npad, n, npad, s));
+      AF2_TRY(launch_pair_bias(x, T, d, w->w_edge, bias, heads, (long long)n * npad, n, npad, s, bias_t ? 1 : 0));
     } else {
       lp.y = nullptr;
       AF2_TRY(launch_layernorm(lp, s));
@@ -828,7 +834,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
   if (has_bias && !fuse_bias && !pre_bias && pair_bias_fast_ok(d, heads)) {
     for (int b = 0; b < B; ++b)
       AF2_TRY(launch_pair_bias(edges + (long long)b * n * n * d, (long long)n * n, d, w->w_edge, bias + (long long)b * heads * n * npad,
-                               heads, (long long)n * npad, n, npad, s));
+                               heads, (long long)n * npad, n, npad, s, bias_t ? 1 : 0));
   } else if (has_bias && !fuse_bias && !pre_bias) {
     for (int b = 0; b < B; ++b) {
       LnParams bp;
@@ -876,7 +882,7 @@ static int axial_attention_impl(const af2_attn_weights* w, float* x, const float
     AF2_TRY(launch_attention(qkv + t0 * 3 * I, heads, dim_head, n, nb, tok_sb, tok_si,
                              has_bias ? bias + (long long)b * heads * n * npad : nullptr, npad,
                              mask ? mask + t0 : nullptr, gate + t0 * I, og + t0 * I, s,
-                             (g_attn_headmajor && dim_head % 8 == 0) ? qkv_hm + t0 * 3 * I : nullptr, Tb));
+                             (g_attn_headmajor && dim_head % 8 == 0) ? qkv_hm + t0 * 3 * I : nullptr, Tb, bias_t ? 1 : 0));
   }
   // 4. to_out + bias + residual
   GemmCall co = linear_call(og, I, w->w_out, I, (int)T, d, (int)I);

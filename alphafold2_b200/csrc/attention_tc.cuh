@@ -56,6 +56,8 @@ struct AttnParams {
   long long tok_sb, tok_si;
   long long ld_gate, ld_out;
   long long* trace;           // debug (AF2_ATTN_TRACE=1): clock64 stamps of CTA 0, 8 per key block, see tools/attn_trace.py
+  int bias_t;                 // 1: the bias is stored transposed, [h][key][query]: its tile is then a K-major B operand of the bias
+                              //    MMA (full tensor rate; the [query][key] tile is MN-major and runs at about half rate)
   int ident_tmem;             // 1: the identity operand of the bias MMA lives in tensor memory (AF2_ATTN_IDENT_TMEM)
   int dbg_skip;               // DEBUG (AF2_ATTN_SKIP): bit 0 skip the V loads, bit 1 the K loads, bit 2 the Q loads, bit 3 the output stores (results wrong; timing experiments only)
   int k_stages3;              // 1: three K stages in resident-bias mode (AF2_ATTN_K3, default on)
@@ -295,8 +297,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_arrive_expect_tx(bias_full, nkv * L::BIAS_BYTES);
           for (int j = 0; j < nkv; ++j) {
             uint8_t* sb = smem + bias_res_off + j * L::BIAS_BYTES;
-            tma_load_3d(sb, &tmBias, bias_full, j * 128, qb * 128, h);
-            tma_load_3d(sb + 16384, &tmBias, bias_full, j * 128 + 64, qb * 128, h);
+            if (p.bias_t) {      // [key rows][query columns]: two 64-query boxes
+              tma_load_3d(sb, &tmBias, bias_full, qb * 128, j * 128, h);
+              tma_load_3d(sb + 16384, &tmBias, bias_full, qb * 128 + 64, j * 128, h);
+            } else {             // [query rows][key columns]: two 64-key boxes
+              tma_load_3d(sb, &tmBias, bias_full, j * 128, qb * 128, h);
+              tma_load_3d(sb + 16384, &tmBias, bias_full, j * 128 + 64, qb * 128, h);
+            }
           }
           ++nc;
         }
@@ -323,8 +330,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_4d(sk, &tmK, &k_full[ks], 0, j * 128, h, b);
           if (stream_bias) {
             uint8_t* sbias = sk + L::KV_BYTES;
-            tma_load_3d(sbias, &tmBias, &k_full[ks], j * 128, qb * 128, h);
-            tma_load_3d(sbias + 16384, &tmBias, &k_full[ks], j * 128 + 64, qb * 128, h);
+            if (p.bias_t) {
+              tma_load_3d(sbias, &tmBias, &k_full[ks], qb * 128, j * 128, h);
+              tma_load_3d(sbias + 16384, &tmBias, &k_full[ks], qb * 128 + 64, j * 128, h);
+            } else {
+              tma_load_3d(sbias, &tmBias, &k_full[ks], j * 128, qb * 128, h);
+              tma_load_3d(sbias + 16384, &tmBias, &k_full[ks], j * 128 + 64, qb * 128, h);
+            }
           }
         }
       }
@@ -415,16 +427,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t sbz = resident ? smem_u32(smem + bias_res_off + j * L::BIAS_BYTES) : sk + L::KV_BYTES;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // B: bias rows (the K index) 16k .. 16k+15 with the keys contiguous (MN-major): 8-row atoms 1024 B apart,
-            // the two 64-key boxes 16 KB apart
-            const uint64_t bd = umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
+            // B, [query][key] tile: bias rows (the K index) 16k .. 16k+15 with the keys contiguous (MN-major): 8-row atoms
+            //    1024 B apart, the two 64-key boxes 16 KB apart;
+            // B, transposed [key][query] tile: K-major like the K tile of Q K^T -- 128-byte rows of 64 queries, 16 queries
+            //    (32 B) per step, the second 64-query box 16 KB further
+            const uint64_t bd = p.bias_t ? umma_smem_desc(sbz + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128)
+                                         : umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
+            const uint32_t idb = p.bias_t ? idesc_s : idesc_b;
             if (p.ident_tmem) {
               // A: identity columns 16k .. 16k+15 from tensor memory (8 packed columns)
-              umma_bf16_ts(tmem_base + S_COL + st * 128, tmem_base + IDENT_COL + k * 8, bd, idesc_b, 1u);
+              umma_bf16_ts(tmem_base + S_COL + st * 128, tmem_base + IDENT_COL + k * 8, bd, idb, 1u);
             } else {
               // A: identity columns 16k .. 16k+15 = the diagonal strip entered (14 - 2k) row groups in (see AttnSmem)
               const uint64_t ad = umma_smem_desc(si + (14 - 2 * k) * 256, 16, 256, SWZ_32);
-              umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idesc_b, 1u);
+              umma_bf16(tmem_base + S_COL + st * 128, ad, bd, idb, 1u);
             }
           }
         }

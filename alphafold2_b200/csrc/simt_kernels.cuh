@@ -199,6 +199,7 @@ struct PairBiasParams {
   long long bias_hs;
   int n_inner, pitch;
   int x_evict_last;         // 1: loads of x carry an L2 evict_last hint (AF2_X_EVICT_LAST)
+  int transpose;            // 1: token t = (i, j) is stored at [j][i] instead of [i][j] (the attention kernel's K-major bias operand)
 };
 
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(256, 3) pair_bias_kernel(const PairBiasParams 
     const float res = (hi1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, hi1 ? r2[0] : r2[1], 1);
     if (live && sub < p.heads) {
       const int ti = static_cast<int>(t);                        // T < 2^31 (checked by the host)
-      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
+      const int ti_i = ti / p.n_inner, ti_j = ti - ti_i * p.n_inner;
+      const long long off = p.transpose ? static_cast<long long>(ti_j) * p.pitch + ti_i : static_cast<long long>(ti_i) * p.pitch + ti_j;
       p.bias_out[sub * p.bias_hs + off] = __float2bfloat16(res);
     }
   }
@@ -319,13 +321,15 @@ __global__ void __launch_bounds__(256, 2) pair_bias_mma_kernel(const PairBiasPar
     const int h0 = 2 * t;
     if (l0) {
       const int ti = static_cast<int>(r0);
-      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
+      const int ti_i = ti / p.n_inner, ti_j = ti - ti_i * p.n_inner;
+      const long long off = p.transpose ? static_cast<long long>(ti_j) * p.pitch + ti_i : static_cast<long long>(ti_i) * p.pitch + ti_j;
       if (h0 < p.heads) p.bias_out[h0 * p.bias_hs + off] = __float2bfloat16(c[0]);
       if (h0 + 1 < p.heads) p.bias_out[(h0 + 1) * p.bias_hs + off] = __float2bfloat16(c[1]);
     }
     if (l1) {
       const int ti = static_cast<int>(r1);
-      const long long off = static_cast<long long>(ti / p.n_inner) * p.pitch + (ti % p.n_inner);
+      const int ti_i = ti / p.n_inner, ti_j = ti - ti_i * p.n_inner;
+      const long long off = p.transpose ? static_cast<long long>(ti_j) * p.pitch + ti_i : static_cast<long long>(ti_i) * p.pitch + ti_j;
       if (h0 < p.heads) p.bias_out[h0 * p.bias_hs + off] = __float2bfloat16(c[2]);
       if (h0 + 1 < p.heads) p.bias_out[(h0 + 1) * p.bias_hs + off] = __float2bfloat16(c[3]);
     }
