@@ -471,7 +471,7 @@ int launch_chan_to_token_tma(const ChanLnParams& p, long long T, cudaStream_t s)
 }
 
 int g_c2t_tma = 1;   // 0: tile-per-CTA kernel (AF2_C2T_TMA=0)
-int g_attn_bias_t = 1;      // 1: pair bias stored transposed ([h][key][query]) so the bias MMA's B operand is K-major (AF2_ATTN_BIAS_T)
+int g_attn_bias_t = 0;      // 1: pair bias stored transposed ([h][key][query]) so the bias MMA's B operand is K-major (AF2_ATTN_BIAS_T)
 int g_attn_ident_tmem = 1;  // 1: bias-MMA identity operand in tensor memory (AF2_ATTN_IDENT_TMEM=0: shared-memory strip)
 int g_attn_skip = 0;       // DEBUG timing experiments (AF2_ATTN_SKIP bitmask, results wrong)
 int g_attn_k3 = 0;         // 1: three K stages in the attention kernel's resident-bias mode (AF2_ATTN_K3)
