@@ -70,7 +70,15 @@ constexpr int ATTN_SM_WARPS = 4 * ATTN_NSPLIT;      // softmax warps 2 .. 2 + AT
 constexpr int ATTN_W_KEYMASK = 2 + ATTN_SM_WARPS;   // then: key-mask warp, V TMA warp, 4 epilogue warps
 constexpr int ATTN_W_VPROD = ATTN_W_KEYMASK + 1;
 constexpr int ATTN_W_EPI = ATTN_W_VPROD + 1;        // a multiple of 4, so warp & 3 is the TMEM lane quarter of an epilogue warp
-constexpr int ATTN_THREADS = (ATTN_W_EPI + 4) * 32;
+// 1: a second MMA-issuing warp (the last one) issues P V while warp 1 issues S.  The timeline of the single issuer
+// (AF2_ATTN_TRACE) showed it 100 % busy: ~1150 cycles issuing the 12 S MMAs (they are accepted at the tensor pipe's pace),
+// ~500 for the 8 P V MMAs and ~1500 of mbarrier / fence round trips per key block -- 3300 cycles, the block period, with the
+// softmax warps (1900 cycles of work) waiting for it.  Two issuers run those chains side by side.
+#ifndef AF2_ATTN_SPLIT_MMA
+#define AF2_ATTN_SPLIT_MMA 1
+#endif
+constexpr int ATTN_W_PV = ATTN_W_EPI + 4;           // the P V issuer (AF2_ATTN_SPLIT_MMA)
+constexpr int ATTN_THREADS = (ATTN_W_EPI + 4 + AF2_ATTN_SPLIT_MMA) * 32;
 static_assert(ATTN_W_EPI % 4 == 0, "epilogue warps must start at a multiple of 4");
 
 template <int DH>
@@ -240,7 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // SW32 strip) the eight K = 16 bias steps took ~1000 cycles per key block -- twice their tensor-pipe time, and the whole S
   // issue (1300 cycles, AF2_ATTN_TRACE) sits on the kernel's critical path between two softmax phases.
   constexpr uint32_t IDENT_COL = 384;
-  if (p.has_bias && p.ident_tmem && warp >= ATTN_W_EPI) {
+  if (p.has_bias && p.ident_tmem && warp >= ATTN_W_EPI && warp < ATTN_W_EPI + 4) {
     const uint32_t r = (warp & 3) * 32 + lane;
     uint32_t v[32];
 #pragma unroll
@@ -470,6 +478,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       return mbar_test(&k_full[sw.kst], sw.kph);
     };
+#if AF2_ATTN_SPLIT_MMA
+    // S issuer.  S(g) overwrites the TMEM buffer that held P(g - 2): it may only be issued once P V(g - 2) has RETIRED (the two
+    // issuers are different threads, so program order no longer orders their MMAs; the V stage's v_empty barrier is committed
+    // behind exactly those MMAs).  That is one softmax phase before S(g) is needed.
+    for (int g = 0; g < total_blocks; ++g) {
+      if (g >= 2) {
+        mbar_wait(&v_empty[pw.kst], pw.kph);            // pw walks two blocks behind here: the stage of P V(g - 2)
+        advance(pw, nst);
+      }
+      issue_s(false);
+    }
+  } else if (warp == ATTN_W_PV) {
+    // ================================ P V issuer ==================================
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, P from tensor memory, V MN-major
+    const int total_blocks = my_items * nkv;
+    int it = 0, j = 0, vst = 0;
+    uint32_t vph = 0;
+    for (int g = 0; g < total_blocks; ++g) {
+      const int st = g & 1;
+      mbar_wait(&p_full[st], (g >> 1) & 1);
+      mbar_wait(&v_full[vst], vph);
+      if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
+      tc_fence_after();
+      if (lane == 0) stamp(g, 2);
+      if (elect_one()) {
+        const uint32_t sv = smem_u32(smem + L::STAGE_OFF + vst * stage_stride + L::K_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A = P [128 rows x 16 keys] = 8 packed columns of the S / P buffer; B = V [key][dh], MN-major: 16 keys = 2 atoms
+          const uint64_t bd = umma_smem_desc(sv + k * 2 * SBO, 16, SBO, SWZ);
+          umma_bf16_ts(tmem_base + O_COL + (it & 1) * 64, tmem_base + S_COL + st * 128 + k * 8, bd, idesc_o, (j != 0 || k != 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[vst]);
+        if (j == nkv - 1) umma_commit(&o_full[it & 1]);
+      }
+      __syncwarp();
+      if (lane == 0) stamp(g, 3);
+      if (++j == nkv) { j = 0; ++it; }
+      if (++vst == nst) { vst = 0; vph ^= 1; }
+    }
+#else
     if (total_blocks > 0) issue_s(false);
     for (int g = 0; g < total_blocks; ++g) {
       const int st = g & 1;
@@ -505,6 +554,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       advance(pw, nst);
       if (!s_issued) issue_s(false);
     }
+#endif
   } else if (warp == ATTN_W_KEYMASK) {
     // ================================ key-mask warp ================================
     // stages, one block ahead of the softmax warps, the additive key term of every 128-key block:
