@@ -77,6 +77,9 @@ constexpr int ATTN_W_EPI = ATTN_W_VPROD + 1;        // a multiple of 4, so warp 
 #ifndef AF2_ATTN_SPLIT_MMA
 #define AF2_ATTN_SPLIT_MMA 1
 #endif
+// S / P buffers in tensor memory: three with two MMA issuers (S(g) then only has to wait for P V(g - 3): a whole softmax
+// phase of slack, so the S issue never sits on the critical path), two with one issuer
+constexpr int ATTN_NSB = AF2_ATTN_SPLIT_MMA ? 3 : 2;
 constexpr int ATTN_W_PV = ATTN_W_EPI + 4;           // the P V issuer (AF2_ATTN_SPLIT_MMA)
 constexpr int ATTN_THREADS = (ATTN_W_EPI + 4 + AF2_ATTN_SPLIT_MMA) * 32;
 static_assert(ATTN_W_EPI % 4 == 0, "epilogue warps must start at a multiple of 4");
@@ -135,8 +138,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* k_empty = bars + 10;   // [4] ... and consumed by the block's S MMAs
   uint64_t* v_full = bars + 14;    // [4] V of a block landed
   uint64_t* v_empty = bars + 18;   // [4] ... and consumed by the block's P V
-  uint64_t* s_full = bars + 22;    // [2]
-  uint64_t* p_full = bars + 24;    // [2] P of the block is in its S buffer
+  uint64_t* s_full = bars + 40;    // [ATTN_NSB]
+  uint64_t* p_full = bars + 43;    // [ATTN_NSB] P of the block is in its S buffer
   // (bars + 26 unused: the P V retirement is observed through v_empty)
   uint64_t* kb_full = bars + 27;   // [2] key-mask terms of a block staged
   uint64_t* kb_empty = bars + 29;  // [2] ... and consumed by the 8 softmax warps
@@ -196,7 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   auto g_phase = [&](int it) { return static_cast<uint32_t>(k3 ? (it & 1) : ((it >> 1) & 1)); };
   const int bias_res_off = L::STAGE_OFF + 2 * L::KV_BYTES;               // resident tiles: + j * BIAS_BYTES
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t S_COL = 0, O_COL = 256;
+  constexpr uint32_t S_COL = 0, O_COL = ATTN_NSB * 128;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmG);
@@ -217,12 +220,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&o_empty[s], 4);
       mbar_init(&g_full[s], 1);
       mbar_init(&g_empty[s], 4);
-      mbar_init(&s_full[s], 1);
       mbar_init(&kb_full[s], 1);
       mbar_init(&kb_empty[s], ATTN_SM_WARPS);
     }
-    mbar_init(&p_full[0], ATTN_SM_WARPS);
-    mbar_init(&p_full[1], ATTN_SM_WARPS);
+    for (int s = 0; s < ATTN_NSB; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], ATTN_SM_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -247,8 +251,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // (column k / 2, low half = even k), written once per CTA.  With the identity read from shared memory (32-byte rows,
   // SW32 strip) the eight K = 16 bias steps took ~1000 cycles per key block -- twice their tensor-pipe time, and the whole S
   // issue (1300 cycles, AF2_ATTN_TRACE) sits on the kernel's critical path between two softmax phases.
-  constexpr uint32_t IDENT_COL = 384;
-  if (p.has_bias && p.ident_tmem && warp >= ATTN_W_EPI && warp < ATTN_W_EPI + 4) {
+  constexpr uint32_t IDENT_COL = O_COL + 128;                    // (only with two S buffers: three fill the 512 columns)
+  const bool ident_tmem = p.ident_tmem != 0 && ATTN_NSB == 2;
+  if (p.has_bias && ident_tmem && warp >= ATTN_W_EPI && warp < ATTN_W_EPI + 4) {
     const uint32_t r = (warp & 3) * 32 + lane;
     uint32_t v[32];
 #pragma unroll
@@ -260,7 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_st_wait();
     tc_fence_before();
   }
-  if (p.has_bias && p.ident_tmem) {
+  if (p.has_bias && ident_tmem) {
     __syncthreads();
     tc_fence_after();
   }
@@ -401,11 +406,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int combo_rem = item0 % p.nbatch;                    // (item0 + sw.it) % nbatch  (one division per kernel)
     bool combo_new = true;                               // the item sw.it is the first of its combo (or the CTA's first item)
     int nc = 0;
+    int s_sb = 0;
     // `probed`: s_ready() has just seen every operand barrier of this block complete (a successful test_wait acquires like a
     // wait), so the waits -- ~100 cycles of SYNCS round trip each on this latency-bound warp -- are skipped
     auto issue_s = [&](bool probed) {
       const int g = sw.g, it = sw.it, j = sw.j, kst = sw.kst;
-      const int st = g & 1;
+      const int st = s_sb;                               // S buffer of this block (g % ATTN_NSB, kept incrementally)
       if (j == 0) {
         if (!probed) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
         if (resident && combo_new) {                       // this CTA's range entered the next (h, query block): new bias tiles
@@ -442,7 +448,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint64_t bd = p.bias_t ? umma_smem_desc(sbz + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, SWZ_128)
                                          : umma_smem_desc(sbz + k * 2048, 16384, 1024, SWZ_128);
             const uint32_t idb = p.bias_t ? idesc_s : idesc_b;
-            if (p.ident_tmem) {
+            if (ident_tmem) {
               // A: identity columns 16k .. 16k+15 from tensor memory (8 packed columns)
               umma_bf16_ts(tmem_base + S_COL + st * 128, tmem_base + IDENT_COL + k * 8, bd, idb, 1u);
             } else {
@@ -468,6 +474,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         combo_new = false;
       }
       advance(sw, nstk);
+      if (++s_sb == ATTN_NSB) s_sb = 0;
     };
     // can S of the next block be issued without blocking?  (Q / bias of a new item and the K stage have landed; the S buffer
     // itself is free by construction: S(g) is issued after P V(g-2), and the tensor core executes in issue order)
@@ -479,12 +486,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       return mbar_test(&k_full[sw.kst], sw.kph);
     };
 #if AF2_ATTN_SPLIT_MMA
-    // S issuer.  S(g) overwrites the TMEM buffer that held P(g - 2): it may only be issued once P V(g - 2) has RETIRED (the two
+    // S issuer.  S(g) overwrites the TMEM buffer that held P(g - ATTN_NSB): it may only be issued once that P V has RETIRED (the two
     // issuers are different threads, so program order no longer orders their MMAs; the V stage's v_empty barrier is committed
-    // behind exactly those MMAs).  That is one softmax phase before S(g) is needed.
+    // behind exactly those MMAs).  With three S buffers that is two softmax phases before S(g) is needed.
     for (int g = 0; g < total_blocks; ++g) {
-      if (g >= 2) {
-        mbar_wait(&v_empty[pw.kst], pw.kph);            // pw walks two blocks behind here: the stage of P V(g - 2)
+      if (g >= ATTN_NSB) {
+        mbar_wait(&v_empty[pw.kst], pw.kph);            // pw walks ATTN_NSB blocks behind here: the stage of P V(g - ATTN_NSB)
         advance(pw, nst);
       }
       issue_s(false);
@@ -493,11 +500,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ================================ P V issuer ==================================
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);    // O = P V, P from tensor memory, V MN-major
     const int total_blocks = my_items * nkv;
-    int it = 0, j = 0, vst = 0;
-    uint32_t vph = 0;
+    int it = 0, j = 0, vst = 0, st = 0;
+    uint32_t vph = 0, sph = 0;
     for (int g = 0; g < total_blocks; ++g) {
-      const int st = g & 1;
-      mbar_wait(&p_full[st], (g >> 1) & 1);
+      mbar_wait(&p_full[st], sph);
       mbar_wait(&v_full[vst], vph);
       if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue has read the item that used this O slot
       tc_fence_after();
@@ -517,6 +523,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) stamp(g, 3);
       if (++j == nkv) { j = 0; ++it; }
       if (++vst == nst) { vst = 0; vph ^= 1; }
+      if (++st == ATTN_NSB) { st = 0; sph ^= 1; }
     }
 #else
     if (total_blocks > 0) issue_s(false);
@@ -668,6 +675,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float NEG_INF = -__int_as_float(0x7f800000);
     // lazy O rescaling (rare): the DH accumulator columns are shared out 16 per slice
     const bool o_owner = hk * 16 < DH;
+    int sb = 0;                            // S / P buffer of the block (g % ATTN_NSB) and the phase of its barriers, incremental
+    uint32_t sph = 0;
 
     for (int it = 0; it < my_items; ++it) {
     bool q_valid = true;
@@ -679,7 +688,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = g & 1;
       mbar_wait(&kb_full[st], (g >> 1) & 1);      // key terms (and, at j == 0, query-mask bytes) staged by the key-mask warp
       if (j == 0) q_valid = qvbuf[(it & 1) * 128 + r] != 0;
-      mbar_wait(&s_full[st], (g >> 1) & 1);
+      mbar_wait(&s_full[sb], sph);
       tc_fence_after();
       if (warp == 2 && lane == 0) stamp(g, 4);
 
@@ -687,7 +696,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float s[KPT];
       {
         uint32_t u[KPT];
-        tmem_ld32(tmem_base + S_COL + st * 128 + hk * KPT + lane_sel, u);
+        tmem_ld32(tmem_base + S_COL + sb * 128 + hk * KPT + lane_sel, u);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < KPT; ++i) s[i] = __uint_as_float(u[i]);
@@ -773,7 +782,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // P_j -> tensor memory: this thread's KPT keys become KPT/2 packed columns of the S buffer.  Those columns held logits
       // of a lower slice, which its owner loaded before the row-max barrier above.
-      tmem_st16(tmem_base + S_COL + st * 128 + hk * (KPT / 2) + lane_sel, pk);
+      tmem_st16(tmem_base + S_COL + sb * 128 + hk * (KPT / 2) + lane_sel, pk);
       if (j == nkv - 1) {
         // hand the item over: its row sums go to the epilogue warps (slot it & 1, free once they have read the item that
         // used it before); the matching O follows through o_full, committed behind the P V this arrival triggers
@@ -784,7 +793,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (warp == 2 && lane == 0) stamp(g, 5);
-      if (lane == 0) mbar_arrive(&p_full[st]);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+      if (++sb == ATTN_NSB) { sb = 0; sph ^= 1; }
     }
     }  // work items
   }
