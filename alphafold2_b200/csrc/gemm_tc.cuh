@@ -364,8 +364,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CPW = 4;                                   // chunks per warp and tile (256 columns / 32 / 2 warps)
     const int total_chunks = my_tiles * CPW;
     auto chunk_coords = [&](int k, int& m0w, int& colc) {    // k-th chunk of this warp's stream
-      const int tile = blockIdx.x + (k / CPW) * gridDim.x;
-      const int mt = (tile / n_tiles) % m_tiles;             // (batch = 1, one column tile: EK_RESID_F32_W launches only)
+      const int mt = blockIdx.x + (k / CPW) * gridDim.x;    // = the tile index: EK_RESID_F32_W launches have batch 1 and ONE column
+                                                             // tile (no run-time divisions on this path: it runs per 32-column chunk)
       m0w = mt * GEMM_BM + q * 32;
       colc = (grp + 2 * (k % CPW)) * 32;
     };

@@ -505,13 +505,18 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   const int my_items = p.balance ? (f1 > f0 ? static_cast<int>((f1 - 1) / ntt - f0 / ntt) + 1 : 0)
                                  : ((total_items > cluster_id) ? (total_items - 1 - cluster_id) / nclusters + 1 : 0);
   const int nkb = p.d / GEMM_BK;
-  auto item_unit = [&](int it) { return p.balance ? static_cast<int>(f0 / ntt) + it : (cluster_id + it * nclusters) / p.nsplit; };
+  // (the 64-bit divisions of the balanced split are done ONCE here: these lambdas are called per item by every warp role,
+  // several times per item by the latency-bound producer warps)
+  const int unit_first = static_cast<int>(f0 / ntt);
+  const int t0_first = static_cast<int>(f0 - static_cast<long long>(unit_first) * ntt);
+  const int t1_last = (f1 > f0) ? static_cast<int>((f1 - 1) % ntt) + 1 : 0;
+  auto item_unit = [&](int it) { return p.balance ? unit_first + it : (cluster_id + it * nclusters) / p.nsplit; };
   auto item_t0 = [&](int it) {
-    if (p.balance) return it == 0 ? static_cast<int>(f0 % ntt) : 0;
+    if (p.balance) return it == 0 ? t0_first : 0;
     return ((cluster_id + it * nclusters) % p.nsplit) * tiles_per_chunk;
   };
   auto item_t1 = [&](int it) {
-    if (p.balance) return it == my_items - 1 ? static_cast<int>((f1 - 1) % ntt) + 1 : ntt;
+    if (p.balance) return it == my_items - 1 ? t1_last : ntt;
     return min(((cluster_id + it * nclusters) % p.nsplit + 1) * tiles_per_chunk, ntt);
   };
   auto seg_of = [&](int nt) {
