@@ -135,21 +135,26 @@ class CudaStageOps:
         return out
 
     @staticmethod
-    def _merge_mn_pieces(Rg: torch.Tensor, pieces: int, d: int):
-        """Gathered MN-major operand [pieces*d, K, w] with w < 64 columns per piece: the kernel's 64-column TMA boxes cannot span
-        pieces, so instead of `pieces` tiny launches the pieces are re-packed once into ONE operand [d, K, pieces*w]
-        (a pass over the gathered tensor, ~10 us at C2) and contracted in a single launch.  w >= 64: addressed in place."""
+    def _merge_mn_pieces(Rg: torch.Tensor, pieces: int, d: int, n_total: int):
+        """Gathered MN-major operand [pieces*d, K, align8(n_total/pieces)] with fewer than 64 columns per piece: the kernel's
+        64-column TMA boxes cannot span pieces, so instead of `pieces` tiny launches the pieces are re-packed once into ONE
+        operand [d, K, align8(n_total)] (a pass over the gathered tensor, ~10 us at C2) and contracted in a single launch.
+        Each piece's alignment padding is dropped on the way: column p*(n_total/pieces)+c of the result is column c of piece p.
+        Pieces of >= 64 columns are addressed in place."""
         K, w = Rg.shape[1], Rg.shape[2]
-        if pieces == 1 or w >= 64 or w % 8:
+        if pieces == 1 or w >= 64:
             return Rg, pieces
-        return Rg.view(pieces, d, K, w).permute(1, 2, 0, 3).reshape(d, K, pieces * w).contiguous(), 1
+        wt = n_total // pieces
+        out = torch.zeros(d, K, _align8(n_total), dtype=Rg.dtype, device=Rg.device)
+        out[:, :, :n_total].view(d, K, pieces, wt).copy_(Rg.view(pieces, d, K, w)[..., :wt].permute(1, 2, 0, 3))
+        return out, 1
 
     def outer_contract_(self, om, x_rows: torch.Tensor, L: torch.Tensor, Rg: torch.Tensor, msa_mask_full, row0: int, pieces: int):
         """x_rows [rows, N, d] += OuterMean; L [d, S, align8(rows)], Rg [pieces*d, S, align8(N/pieces)]."""
         pk = om.packed()
         rows, N, d = x_rows.shape
         S = L.shape[1]
-        Rg, pieces = self._merge_mn_pieces(Rg, pieces, d)
+        Rg, pieces = self._merge_mn_pieces(Rg, pieces, d, N)
         lib = _lib.load()
         ws = _ops.workspace(lib.af2_outer_contract_workspace(rows, N, d), x_rows.device)
         mk = None if msa_mask_full is None else msa_mask_full.contiguous()
@@ -179,7 +184,7 @@ class CudaStageOps:
         rows, cols, d = x_loc.shape
         K = L.shape[1] if ingoing else cols
         if ingoing:
-            Rg, pieces = self._merge_mn_pieces(Rg, pieces, d)
+            Rg, pieces = self._merge_mn_pieces(Rg, pieces, d, rows)
         lib = _lib.load()
         ws = _ops.workspace(lib.af2_triangle_contract_workspace(rows, cols, d), x_loc.device)
         per_piece = Rg.numel() // pieces

@@ -19,7 +19,7 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
-    for (d, H, dh, N, S, masked) in [(64, 2, 32, 48, 8, True), (256, 8, 64, 128, 16, False), (256, 8, 64, 256, 128, True)]:
+    for (d, H, dh, N, S, masked) in [(64, 2, 32, 48, 8, True), (64, 2, 32, 40, 8, False), (256, 8, 64, 128, 16, False), (256, 8, 64, 256, 128, True)]:
         torch.manual_seed(0)
         evo = A.Evoformer(depth=2, dim=d, seq_len=N, heads=H, dim_head=dh, attn_dropout=0., ff_dropout=0.)
         st = O.randomize_zero_init_({k: v.clone() for k, v in evo.state_dict().items()}, std=0.05)

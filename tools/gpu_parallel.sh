@@ -1,11 +1,12 @@
 #!/bin/bash
 # N-GPU check of the sharded trunk + scaling bench (an N-GPU gpurun call is charged N x its wall time: keep the timeouts tight)
-# usage: tools/gpu_parallel.sh <N> <tag> [C4]
+# usage: [ONLY_CHECK=1] tools/gpu_parallel.sh <N> <tag> [C4]
 N=${1:-2}; TAG=${2:-r02}; BIG=${3:-}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 240 $TR --master-port 29551 tests/parallel_check_multi_gpu.py > gpurun_out/parallel_check_${N}gpu_${TAG}.log 2>&1; echo "parallel_check rc=$?"
 grep -E '^\{' gpurun_out/parallel_check_${N}gpu_${TAG}.log | cut -c1-330 | head -6; grep -v '^{' gpurun_out/parallel_check_${N}gpu_${TAG}.log | tail -4
+[ -n "$ONLY_CHECK" ] && exit 0
 timeout 200 $TR --master-port 29552 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_C2_${N}gpu_${TAG}.json 2> gpurun_out/bench_C2_${N}gpu_${TAG}.err; echo "bench C2 N=$N rc=$?"; tail -2 gpurun_out/bench_C2_${N}gpu_${TAG}.err
 if [ "$N" -le 2 ]; then
   AF2_GATHER_FUSED=0 timeout 200 $TR --master-port 29553 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_C2_${N}gpu_pieces_${TAG}.json 2> /dev/null; echo "bench C2 N=$N (per-piece launches) rc=$?"
