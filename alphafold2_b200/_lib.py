@@ -99,6 +99,16 @@ _SIGNATURES = {
     "af2_l2_persist": (ci, [vp, ll, cf, vp]),
     "af2_split_bf16": (ci, [vp, vp, ll, ci, vp]),
     "af2_gemm_split_f32": (ci, [vp, vp, vp, ll, ci, ci, ci, ci, vp]),
+    # peer-memory exchange of the sharded trunk
+    "af2_peer_ctrl_bytes": (ci, []),
+    "af2_peer_can_access": (ci, [ci, ci]),
+    "af2_peer_alloc": (ci, [ll, C.POINTER(vp)]),
+    "af2_peer_free": (ci, [vp]),
+    "af2_peer_export": (ci, [vp, vp]),
+    "af2_peer_open": (ci, [vp, C.POINTER(vp)]),
+    "af2_peer_close": (ci, [vp]),
+    "af2_peer_error": (ci, [vp]),
+    "af2_peer_exchange": (ci, [vp, ll, ll, vp, ll, ll, ci, ll, ci, ci, ci, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

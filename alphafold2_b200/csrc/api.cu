@@ -1375,3 +1375,4 @@ int af2_gemm_bf16_f32(const void* A, long long lda, long long a_batch, const voi
 }  // extern "C"
 
 #include "strict_api.inl"
+#include "peer_api.inl"

@@ -19,6 +19,7 @@ schedule itself (slicing, layouts, collectives) under gloo with world_size 2.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Optional
 
@@ -65,10 +66,20 @@ def cols_to_rows(t_col: torch.Tensor, group) -> torch.Tensor:
 
 class _Deferred:
     """cols_to_rows on a side stream: the MSA tensor goes back to row shards while the pair track of the same block runs
-    (nothing reads it before the next block's row attention).  The collective itself runs on the process group's NCCL
-    stream either way; what the side stream removes is the main stream's wait for it.  `get()` joins."""
+    (nothing reads it before the next block's row attention).  With NCCL the collective itself runs on the process
+    group's stream either way and the side stream removes the main stream's wait for it; with the peer-memory exchange
+    (ex) the exchange kernel itself runs on the side stream, on barrier channel 1.  `get()` joins."""
 
-    def __init__(self, t_col: torch.Tensor, group, side):
+    def __init__(self, t_col: torch.Tensor, group, side, ex=None):
+        cur = torch.cuda.current_stream()
+        if ex is not None:
+            ready = cur.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                self.out = ex.cols_to_rows(t_col, PeerExchange.MSA, channel=1)
+                self.done = side.record_event()
+            self.keep = self.bufs = None
+            return
         P = dist.get_world_size(group)
         RR, Cl, d = t_col.shape
         R = RR // P
@@ -77,7 +88,6 @@ class _Deferred:
         recv = torch.empty_like(send)                                         # allocated on the main stream: its pool, its ordering
         self.out = torch.empty(R, P * Cl, d, dtype=t_col.dtype, device=t_col.device)
         self.bufs = (send, recv)
-        cur = torch.cuda.current_stream()
         ready = cur.record_event()
         with torch.cuda.stream(side):
             side.wait_event(ready)
@@ -89,6 +99,183 @@ class _Deferred:
         torch.cuda.current_stream().wait_event(self.done)
         out, self.keep, self.bufs = self.out, None, None
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# peer-memory exchange: the row <-> column re-layouts as ONE kernel storing into the destination ranks' memory (NVLink)
+# ------------------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """A cudaMalloc'ed range presented to torch through the CUDA array interface (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+
+
+PEER_EXCHANGE_ENABLED = os.environ.get("AF2_PEER_EXCHANGE", "1") not in ("", "0")
+_PEER_ARENAS = {}           # (id(group), device index, N, S, d) -> PeerExchange | None (None: tried, not available)
+
+
+class PeerExchange:
+    """Row-shard <-> column-shard exchange of the pair and MSA tensors through peer memory (csrc/peer_api.inl).
+
+    Every rank allocates one arena holding, for each of the two tracks, a row-layout buffer [R, C, d] and a column-layout
+    buffer [P*R, C/P, d] (fp32), and maps the other ranks' arenas with CUDA IPC.  `rows_to_cols` / `cols_to_rows` launch one
+    kernel that stores every chunk into its destination rank's buffer and joins a flag barrier; the returned tensor IS the
+    local destination buffer.  The schedule strictly alternates the two layouts of a track, which is what makes one
+    barrier per exchange sufficient: a rank starts writing a peer's buffer X only after that peer signalled the barrier
+    of the exchange in which it last read X.  Single node only (IPC); `create` returns None when peer access, IPC or
+    the array-interface wrapping is not available on every rank, and the schedule then uses NCCL all_to_all."""
+
+    PAIR, MSA = 0, 1
+
+    def __init__(self):
+        self.base = None
+        self.opened = []
+
+    @classmethod
+    def create(cls, group, device: torch.device, N: int, S: int, d: int):
+        P, r = dist.get_world_size(group), dist.get_rank(group)
+        lib = _lib.load()
+        self = cls()
+        self.group, self.P, self.rank, self.device = group, P, r, device
+        ctrl = int(lib.af2_peer_ctrl_bytes())
+        al = lambda n: (n + 255) // 256 * 256  # noqa: E731
+        pair_b, msa_b = al(N // P * N * d * 4), al(S // P * N * d * 4)
+        self.off = {(cls.PAIR, "row"): ctrl, (cls.PAIR, "col"): ctrl + pair_b,
+                    (cls.MSA, "row"): ctrl + 2 * pair_b, (cls.MSA, "col"): ctrl + 2 * pair_b + msa_b}
+        total = ctrl + 2 * pair_b + 2 * msa_b
+        ok = P <= 32 and device.type == "cuda"
+        handle = torch.zeros(72, dtype=torch.uint8)
+        # 1. local arena + IPC handle (no collective inside: every rank reaches the all_gather below whatever happens here)
+        try:
+            if ok:
+                base = C.c_void_p()
+                _lib.check(lib.af2_peer_alloc(total, C.byref(base)))
+                self.base = base.value
+                hb = (C.c_ubyte * 64)()
+                _lib.check(lib.af2_peer_export(self.base, hb))
+                handle[:64] = torch.frombuffer(bytearray(hb), dtype=torch.uint8)
+                handle[64] = 1
+                handle[65] = device.index
+                self.arena = torch.as_tensor(_RawCuda(self.base, total), device=device)
+                if self.arena.data_ptr() != self.base:
+                    raise RuntimeError("array-interface wrapping copied the arena")
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            self.why = f"{type(e).__name__}: {e}"
+        if not ok:
+            handle[64] = 0
+        # 2. everyone's handle
+        allh = torch.empty(P * 72, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, handle.to(device), group=group)
+        allh = allh.cpu().view(P, 72)
+        ok = ok and bool((allh[:, 64] == 1).all())
+        # 3. map the peers
+        bases = [0] * P
+        if ok:
+            try:
+                for p in range(P):
+                    if p == r:
+                        bases[p] = self.base
+                        continue
+                    if not lib.af2_peer_can_access(device.index, int(allh[p, 65])):
+                        raise RuntimeError(f"no peer access from device {device.index} to device {int(allh[p, 65])}")
+                    hb = (C.c_ubyte * 64)(*allh[p, :64].tolist())
+                    ptr = C.c_void_p()
+                    _lib.check(lib.af2_peer_open(hb, C.byref(ptr)))
+                    self.opened.append(ptr.value)
+                    bases[p] = ptr.value
+            except Exception as e:  # noqa: BLE001
+                ok = False
+                self.why = f"{type(e).__name__}: {e}"
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if not int(flag.item()):
+            why = getattr(self, "why", "another rank could not set it up")
+            import sys
+            print(f"[alphafold2_b200.parallel] rank {r}: peer-memory exchange not available ({why}); using NCCL all_to_all", file=sys.stderr)
+            self._release_local()
+            return None
+        self.table = torch.tensor(bases, dtype=torch.int64, device=device)            # device array of the P arena bases
+        self.shapes = {(cls.PAIR, "row"): (N // P, N, d), (cls.PAIR, "col"): (N, N // P, d),
+                       (cls.MSA, "row"): (S // P, N, d), (cls.MSA, "col"): (S, N // P, d)}
+        self.exchanges = 0
+        return self
+
+    def buffer(self, track: int, layout: str) -> torch.Tensor:
+        shape = self.shapes[(track, layout)]
+        n = shape[0] * shape[1] * shape[2] * 4
+        o = self.off[(track, layout)]
+        return self.arena[o:o + n].view(torch.float32).view(shape)
+
+    def _exchange(self, src: torch.Tensor, src_peer_stride, src_row_stride, dst_off, dst_row_stride, rows, row_bytes, channel):
+        _lib.check(_lib.load().af2_peer_exchange(src.data_ptr(), src_peer_stride, src_row_stride, self.table.data_ptr(), dst_off,
+                                                  dst_row_stride, rows, row_bytes, channel, self.rank, self.P, _ops._stream_ptr()))
+        self.exchanges += 1
+
+    def rows_to_cols(self, t_row: torch.Tensor, track: int, channel: int = 0) -> torch.Tensor:
+        """[R, C, d] (my rows, all columns; the track's row buffer) -> the track's column buffer [P*R, C/P, d]."""
+        R, Cc, d = t_row.shape
+        chunk = Cc // self.P * d * 4
+        assert t_row.data_ptr() == self.base + self.off[(track, "row")] and tuple(t_row.shape) == self.shapes[(track, "row")]
+        self._exchange(t_row, chunk, Cc * d * 4, self.off[(track, "col")] + self.rank * R * chunk, chunk, R, chunk, channel)
+        return self.buffer(track, "col")
+
+    def cols_to_rows(self, t_col: torch.Tensor, track: int, channel: int = 0) -> torch.Tensor:
+        """[P*R, Cl, d] (all rows, my columns; the track's column buffer) -> the track's row buffer [R, P*Cl, d]."""
+        RR, Cl, d = t_col.shape
+        R, chunk = RR // self.P, Cl * d * 4
+        assert t_col.data_ptr() == self.base + self.off[(track, "col")] and tuple(t_col.shape) == self.shapes[(track, "col")]
+        self._exchange(t_col, R * chunk, chunk, self.off[(track, "row")] + self.rank * chunk, self.P * chunk, R, chunk, channel)
+        return self.buffer(track, "row")
+
+    def error(self) -> bool:
+        return bool(self.base) and bool(_lib.load().af2_peer_error(self.base))
+
+    def _release_local(self):
+        lib = _lib.load()
+        for ptr in self.opened:
+            lib.af2_peer_close(ptr)
+        self.opened = []
+        self.arena = None
+        if self.base:
+            lib.af2_peer_free(self.base)
+            self.base = None
+
+    def close(self):
+        """Collective: unmap the peers, then free the arena (a rank frees only after everyone has unmapped it)."""
+        if self.base is None:
+            return
+        torch.cuda.synchronize()
+        lib = _lib.load()
+        for ptr in self.opened:
+            lib.af2_peer_close(ptr)
+        self.opened = []
+        try:
+            dist.barrier(group=self.group)
+        except Exception:  # noqa: BLE001 - process group already gone: the driver reclaims the mappings at exit
+            pass
+        self._release_local()
+
+
+def peer_exchange_for(group, device: torch.device, N: int, S: int, d: int):
+    """The arena for this (group, shape), created on first use (collectively: every rank makes the same calls)."""
+    if not PEER_EXCHANGE_ENABLED or device.type != "cuda" or dist.get_backend(group) != "nccl" or dist.get_world_size(group) < 2:
+        return None
+    key = (id(group), device.index, N, S, d)
+    if key not in _PEER_ARENAS:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        _PEER_ARENAS[key] = PeerExchange.create(group, device, N, S, d)
+        _hook_teardown()
+    return _PEER_ARENAS[key]
+
+
+def release_peer_arenas() -> None:
+    for key in list(_PEER_ARENAS):
+        ex = _PEER_ARENAS.pop(key)
+        if ex is not None:
+            ex.close()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -215,8 +402,20 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
         raise ValueError(f"N_res={N} and N_seq={S} must be divisible by the number of ranks {P}")
     Rn, Rs = N // P, S // P
     with torch.no_grad():
-        x_row = x[0, r * Rn:(r + 1) * Rn].detach().to(torch.float32).contiguous().clone()      # [N/P, N, d]
-        m_row = m[0, r * Rs:(r + 1) * Rs].detach().to(torch.float32).contiguous().clone()      # [S/P, N, d]
+        ex = peer_exchange_for(group, x.device, N, S, x.shape[-1]) if stage_ops is None else None
+        if ex is not None:                                            # the shards live in the peer-mapped arena
+            x_row, m_row = ex.buffer(PeerExchange.PAIR, "row"), ex.buffer(PeerExchange.MSA, "row")
+            x_row.copy_(x[0, r * Rn:(r + 1) * Rn])
+            m_row.copy_(m[0, r * Rs:(r + 1) * Rs])
+            pair_to_cols = lambda t: ex.rows_to_cols(t, PeerExchange.PAIR)  # noqa: E731
+            pair_to_rows = lambda t: ex.cols_to_rows(t, PeerExchange.PAIR)  # noqa: E731
+            msa_to_cols = lambda t: ex.rows_to_cols(t, PeerExchange.MSA)  # noqa: E731
+            msa_to_rows = lambda t: ex.cols_to_rows(t, PeerExchange.MSA)  # noqa: E731
+        else:
+            x_row = x[0, r * Rn:(r + 1) * Rn].detach().to(torch.float32).contiguous().clone()      # [N/P, N, d]
+            m_row = m[0, r * Rs:(r + 1) * Rs].detach().to(torch.float32).contiguous().clone()      # [S/P, N, d]
+            pair_to_cols = msa_to_cols = lambda t: rows_to_cols(t, group)  # noqa: E731
+            pair_to_rows = msa_to_rows = lambda t: cols_to_rows(t, group)  # noqa: E731
         mask_full = None if mask is None else mask[0].bool()
         mm_full = None if msa_mask is None else msa_mask[0].bool().contiguous()
         mask_rows = None if mask_full is None else mask_full[r * Rn:(r + 1) * Rn].contiguous()
@@ -240,7 +439,7 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
             if pending is not None:
                 m_row, pending = pending.get(), None
             ops.axial_attention_(msa_attn.row_attn, m_row, bias_m, mm_rows, True)
-            m_col = rows_to_cols(m_row, group)                                           # [S, N/P, d]
+            m_col = msa_to_cols(m_row)                                                  # [S, N/P, d]
             ops.axial_attention_(msa_attn.col_attn, m_col, None, mm_cols, False)
             ops.feed_forward_(msa_ff, m_col)
             # --- outer mean into the pair rows (alphafold2.py:379) ---
@@ -248,35 +447,35 @@ def sharded_evoformer_forward(evo, x: torch.Tensor, m: torch.Tensor, mask: Optio
             Rg = all_gather_cat0(LR[d:], group)                                          # [P*d, S, pitch]
             ops.outer_contract_(pair.outer_mean, x_row, LR[:d], Rg, mm_full, r * Rn, P)
             if overlap:
-                pending = _Deferred(m_col, group, side)                                  # joins at the next block's row attention
+                pending = _Deferred(m_col, group, side, ex)                             # joins at the next block's row attention
             else:
-                m_row = cols_to_rows(m_col, group)
+                m_row = msa_to_rows(m_col)
             # --- triangle multiply outgoing on pair rows (alphafold2.py:381) ---
             tm = pair.triangle_multiply_outgoing
             L, R, G = ops.tri_project(tm, x_row, mask_rows)
             ops.tri_contract_(tm, x_row, L, all_gather_cat0(R, group), G, False, P)
             # --- triangle multiply ingoing on pair columns (alphafold2.py:382) ---
-            x_col = rows_to_cols(x_row, group)                                           # [N, N/P, d]
+            x_col = pair_to_cols(x_row)                                                  # [N, N/P, d]
             tm = pair.triangle_multiply_ingoing
             L, R, G = ops.tri_project(tm, x_col, mask_cols)
             ops.tri_contract_(tm, x_col, L, all_gather_cat0(R, group), G, True, P)
             # --- triangle attention outgoing = row attention on pair rows (alphafold2.py:383) ---
-            x_row = cols_to_rows(x_col, group)
+            x_row = pair_to_rows(x_col)
             ta = pair.triangle_attention_outgoing
             ops.axial_attention_(ta, x_row, gathered_bias(ta, x_row), mask_rows, True)
             # --- triangle attention ingoing = column attention on pair columns (alphafold2.py:384) ---
             ta = pair.triangle_attention_ingoing
             bias = gathered_bias(ta, x_row)
-            x_col = rows_to_cols(x_row, group)
+            x_col = pair_to_cols(x_row)
             ops.axial_attention_(ta, x_col, bias, mask_cols, False)
             # --- pair transition (pointwise), back to rows (alphafold2.py:444) ---
             ops.feed_forward_(ff, x_col)
-            x_row = cols_to_rows(x_col, group)
+            x_row = pair_to_rows(x_col)
 
         if pending is not None:
             m_row, pending = pending.get(), None
         if not gather_output:
-            return x_row, m_row
+            return (x_row.clone(), m_row.clone()) if ex is not None else (x_row, m_row)   # arena buffers are reused by the next call
         xo = all_gather_cat0(x_row, group)[None]
         mo = all_gather_cat0(m_row, group)[None]
     return xo.to(x.dtype), mo.to(m.dtype)
@@ -308,6 +507,7 @@ def release_all_graphs() -> None:
         g.release()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
+    release_peer_arenas()
 
 
 def _hook_teardown() -> None:

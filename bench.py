@@ -122,6 +122,16 @@ def randomize_zero_init_(model, std=0.02, seed=1234):
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference (the Python reference itself cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------------------------
+def exchange_transport():
+    """How the sharded schedule moved its row<->column re-layouts in this run (alphafold2_b200/parallel.py)."""
+    from alphafold2_b200 import parallel as _p
+    live = [ex for ex in _p._PEER_ARENAS.values() if ex is not None]
+    if live:
+        return {"all_to_all": "peer-store kernel over CUDA IPC mappings (af2_peer_exchange)", "exchanges": sum(ex.exchanges for ex in live),
+                "barrier_timeouts": int(any(ex.error() for ex in live)), "all_gather": "NCCL"}
+    return {"all_to_all": "NCCL all_to_all_single + pack/unpack copies", "all_gather": "NCCL"}
+
+
 def host_threads():
     """All the host CORES the CPU arm can use.  torchrun exports OMP_NUM_THREADS=1 to its workers (round 1's N>1 CPU arm ran
     on one thread), so the count is set explicitly -- to the PHYSICAL cores: with one thread per hyper-thread (128 on the
@@ -461,6 +471,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "replicas": replicas,
         "collectives_per_block": (None if world == 1 else {"all_gather_small_bias": 3, "all_gather_operand": 3, "all_to_all_msa": 2, "all_to_all_pair": 4}),
+        "exchange": (None if world == 1 else exchange_transport()),
         "roofline": roof,
         "roofline_whole_step": {"bound": "tensor", "achieved": step_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                                 "frac": step_tf / peaks["tflops"], "frac_of_burst_peak": step_tf / peaks["tflops_burst"],

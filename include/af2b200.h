@@ -245,6 +245,28 @@ int af2_distogram_head(const float* x, const float* gamma, const float* beta, co
  * persisting in L2 (cudaAccessPolicyWindow; clipped to the device's set-aside / window limits).  ptr == NULL clears it. */
 int af2_l2_persist(const void* ptr, long long bytes, float hit_ratio, af2_stream_t stream);
 
+/* ---- peer-memory exchange for the sharded trunk (alphafold2_b200/parallel.py; no reference counterpart: the reference
+ * has no multi-GPU path) ----
+ * Every rank owns one arena (af2_peer_alloc: cudaMalloc, zeroed; the first af2_peer_ctrl_bytes() bytes are the barrier
+ * control block) which the other ranks of the node map with CUDA IPC (export -> 64-byte handle -> open).  One
+ * af2_peer_exchange launch re-lays a row shard out as column shards (or back): chunk p = `rows` rows of `row_bytes`
+ * contiguous bytes, read at src + p*src_peer_stride + row*src_row_stride, stored into rank p's arena at
+ * dst_off + row*dst_row_stride, followed inside the same kernel by a flag barrier over all P ranks (channel 0 or 1: two
+ * exchanges may be in flight on two streams).  peer_base is a DEVICE array of the P arena bases as mapped in this
+ * process (own arena at index `rank`).  Every rank must issue the same sequence of exchanges per channel.
+ * af2_peer_error returns 1 if a barrier ever gave up waiting (20 s) for a rank. */
+int af2_peer_ctrl_bytes(void);
+int af2_peer_can_access(int device, int peer_device);
+int af2_peer_alloc(long long bytes, void** ptr);
+int af2_peer_free(void* ptr);
+int af2_peer_export(const void* ptr, unsigned char* handle64);
+int af2_peer_open(const unsigned char* handle64, void** ptr);
+int af2_peer_close(void* ptr);
+int af2_peer_error(const void* my_base);
+int af2_peer_exchange(const void* src, long long src_peer_stride, long long src_row_stride, void* const* peer_base,
+                      long long dst_off, long long dst_row_stride, int rows, long long row_bytes, int channel, int rank, int P,
+                      af2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,13 @@ def main():
         res["ok"] = bool(good)
         ok = ok and good
         print(json.dumps(res), flush=True)
+    from alphafold2_b200 import parallel as par
+    live = [ex for ex in par._PEER_ARENAS.values() if ex is not None]
+    timeouts = any(ex.error() for ex in live)
+    if rank == 0:
+        print(json.dumps({"exchange": "peer-store kernel" if live else "nccl all_to_all", "arenas": len(par._PEER_ARENAS),
+                          "barrier_timeouts": bool(timeouts)}), flush=True)
+    ok = ok and not timeouts
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
