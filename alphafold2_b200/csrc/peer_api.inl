@@ -13,7 +13,7 @@
 namespace af2 {
 
 constexpr int PEER_CTRL_BYTES = 4096;
-constexpr int PEER_SEG = 16384;          // bytes of one row a CTA moves (256 threads x 4 x 16 B)
+constexpr int PEER_VEC = 4;              // 16-byte vectors per thread: a CTA moves 256 x PEER_VEC x 16 B of one row
 constexpr int PEER_MAX_RANKS = 32;
 
 struct PeerExchangeParams {
@@ -24,7 +24,7 @@ struct PeerExchangeParams {
   long long dst_off;            // where this rank's chunk starts inside the destination arena
   long long dst_row_stride;
   long long row_bytes;          // contiguous bytes per row (multiple of 16)
-  int rank, P, channel;
+  int rank, P, channel, interleave;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -41,32 +41,40 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// grid (ceil(row_bytes / PEER_SEG), rows, P); block 256.  CTA (x, y, z) moves segment x of row y of the chunk bound for
-// rank (z + rank) % P - at any moment the P senders address P different receivers.  The CTA that finishes last signals
+// grid (segments x P, rows); block 256.  A CTA moves one segment of one row of the chunk bound for one rank; the
+// destination is rotated by the sender's rank so that the P senders address P different receivers at any moment.  The CTA that finishes last signals
 // "my stores are done" to every rank (release, system scope) and waits for the same signal from every rank, so when the
 // kernel completes every chunk bound for THIS rank has landed and the stream's next kernel may read the buffer.
+template <int V, bool FENCE_ALL>
 __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerExchangeParams p) {
-  const int peer = (int)((blockIdx.z + p.rank) % p.P);
-  const long long off0 = (long long)blockIdx.x * PEER_SEG + threadIdx.x * 16;
+  // interleave: the destination rank is the fastest-varying CTA index, so the CTAs resident at any moment address all
+  // P ranks (the local copy overlaps the NVLink stores); otherwise the grid walks the destinations one after another
+  const int peer = p.interleave ? (int)((blockIdx.x % p.P + p.rank) % p.P) : (int)((blockIdx.z + p.rank) % p.P);
+  const unsigned seg_i = p.interleave ? blockIdx.x / p.P : blockIdx.x;
+  const long long off0 = (long long)seg_i * (V * 4096) + threadIdx.x * 16;
   const char* s = p.src + (long long)peer * p.src_peer_stride + (long long)blockIdx.y * p.src_row_stride;
   char* d = p.peer_base[peer] + p.dst_off + (long long)blockIdx.y * p.dst_row_stride;
-  uint4 v[4];
+  uint4 v[V];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < V; ++i) {
     const long long o = off0 + i * 4096;
     if (o < p.row_bytes) v[i] = *reinterpret_cast<const uint4*>(s + o);
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < V; ++i) {
     const long long o = off0 + i * 4096;
     if (o < p.row_bytes) *reinterpret_cast<uint4*>(d + o) = v[i];
   }
-  __threadfence_system();
+  // FENCE_ALL: every thread makes its own stores visible system-wide before the CTA counts itself done.  Otherwise the
+  // CTA barrier orders the stores before thread 0, whose system-scope fence is cumulative over them (PTX memory model:
+  // bar.sync synchronises the CTA's threads, the fence then covers every write that happened before it in causality order).
+  if (FENCE_ALL) __threadfence_system();
   __syncthreads();
   __shared__ int is_last;
   char* mine = p.peer_base[p.rank];
   unsigned* done = reinterpret_cast<unsigned*>(mine + 1088) + p.channel;
   if (threadIdx.x == 0) {
+    if (!FENCE_ALL) __threadfence_system();
     const unsigned total = gridDim.x * gridDim.y * gridDim.z;
     is_last = atomicAdd(done, 1u) == total - 1;
   }
@@ -176,10 +184,21 @@ int af2_peer_exchange(const void* src, long long src_peer_stride, long long src_
   p.src = static_cast<const char*>(src); p.src_peer_stride = src_peer_stride; p.src_row_stride = src_row_stride;
   p.peer_base = reinterpret_cast<char* const*>(peer_base); p.dst_off = dst_off; p.dst_row_stride = dst_row_stride;
   p.row_bytes = row_bytes; p.rank = rank; p.P = P; p.channel = channel;
-  dim3 grid((unsigned)((row_bytes + PEER_SEG - 1) / PEER_SEG), (unsigned)rows, (unsigned)P);
+  const char* ev = getenv("AF2_PEER_VARIANT");   // experiment knob (tools/peer_bench.py): bit 0 = 8 vectors per thread, bit 1 = one fence per CTA, bit 2 = destinations one after another
+  const int variant = ev ? atoi(ev) : 2;    // default: 4 vectors per thread, one fence per CTA, destinations interleaved (profiles/r02p_peer_bench_2gpu.log)
+  const int vec = (variant & 1) ? 8 : PEER_VEC;
+  const long long seg = (long long)vec * 4096;
+  p.interleave = (variant & 4) ? 0 : 1;
+  const unsigned nseg = (unsigned)((row_bytes + seg - 1) / seg);
+  dim3 grid(p.interleave ? nseg * P : nseg, (unsigned)rows, p.interleave ? 1u : (unsigned)P);
   const double bytes = (double)rows * (double)row_bytes * P;
   ProfScope ps(s, 5, 0.0, 2.0 * bytes);
-  peer_exchange_kernel<<<grid, 256, 0, s>>>(p);
+  switch (variant & 3) {
+    case 1: peer_exchange_kernel<8, true><<<grid, 256, 0, s>>>(p); break;
+    case 2: peer_exchange_kernel<PEER_VEC, false><<<grid, 256, 0, s>>>(p); break;
+    case 3: peer_exchange_kernel<8, false><<<grid, 256, 0, s>>>(p); break;
+    default: peer_exchange_kernel<PEER_VEC, true><<<grid, 256, 0, s>>>(p); break;
+  }
   CUDA_OK(cudaGetLastError());
   return AF2_OK;
 }
