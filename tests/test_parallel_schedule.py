@@ -69,3 +69,28 @@ def test_sharded_schedule(masked, world):
         assert p.exitcode == 0
     for rank, ex, em in res:
         assert ex < 1e-4 and em < 1e-4, f"rank {rank}: pair err {ex}, msa err {em}"
+
+
+def test_merge_gathered_pieces_drops_alignment_padding():
+    """CudaStageOps._merge_mn_pieces (host logic, no GPU): P gathered pieces [d, K, align8(w)] become one operand
+    [d, K, align8(P*w)] whose column p*w + c is column c of piece p -- the padding columns of every piece are dropped
+    (they were kept once: wrong pair rows at 8 GPUs whenever N/P is not a multiple of 8)."""
+    import torch
+
+    from alphafold2_b200.parallel import CudaStageOps, _align8
+    for (n_total, P, d, K) in [(48, 8, 4, 3), (40, 2, 3, 5), (64, 8, 2, 2), (256, 8, 2, 4)]:
+        w = n_total // P
+        full = torch.arange(d * K * n_total, dtype=torch.float32).view(d, K, n_total)
+        pieces = []
+        for p in range(P):
+            t = torch.full((d, K, _align8(w)), -1.0)
+            t[..., :w] = full[..., p * w:(p + 1) * w]
+            pieces.append(t)
+        Rg = torch.cat(pieces, 0)
+        merged, n_pieces = CudaStageOps._merge_mn_pieces(Rg, P, d, n_total)
+        assert n_pieces == 1 and merged.shape == (d, K, _align8(n_total))
+        assert torch.equal(merged[..., :n_total], full)
+        assert (merged[..., n_total:] == 0).all()
+    wide = torch.zeros(8 * 2, 3, 64)
+    same, n_pieces = CudaStageOps._merge_mn_pieces(wide, 8, 2, 512)          # >= 64 columns per piece: addressed in place
+    assert same is wide and n_pieces == 8
