@@ -194,6 +194,8 @@ class PeerExchange:
             why = getattr(self, "why", "another rank could not set it up")
             import sys
             print(f"[alphafold2_b200.parallel] rank {r}: peer-memory exchange not available ({why}); using NCCL all_to_all", file=sys.stderr)
+            self._unmap_peers()
+            dist.barrier(group=group)              # nobody frees an arena a peer still has mapped
             self._release_local()
             return None
         self.table = torch.tensor(bases, dtype=torch.int64, device=device)            # device array of the P arena bases
@@ -232,11 +234,15 @@ class PeerExchange:
     def error(self) -> bool:
         return bool(self.base) and bool(_lib.load().af2_peer_error(self.base))
 
-    def _release_local(self):
+    def _unmap_peers(self):
         lib = _lib.load()
         for ptr in self.opened:
             lib.af2_peer_close(ptr)
         self.opened = []
+
+    def _release_local(self):
+        lib = _lib.load()
+        self._unmap_peers()
         self.arena = None
         if self.base:
             lib.af2_peer_free(self.base)
@@ -247,10 +253,7 @@ class PeerExchange:
         if self.base is None:
             return
         torch.cuda.synchronize()
-        lib = _lib.load()
-        for ptr in self.opened:
-            lib.af2_peer_close(ptr)
-        self.opened = []
+        self._unmap_peers()
         try:
             dist.barrier(group=self.group)
         except Exception:  # noqa: BLE001 - process group already gone: the driver reclaims the mappings at exit
@@ -499,7 +502,7 @@ def graph_default() -> bool:
     return os.environ.get("AF2_SHARD_GRAPH", "1") not in ("", "0")
 
 
-def release_all_graphs() -> None:
+def release_all_graphs(peer_arenas: bool = True) -> None:
     """Drop every captured graph of this process.  A process that still owns a CUDA graph with NCCL nodes hangs when the
     communicator is torn down (torch 2.11 / NCCL 2.28.9), so this runs automatically before
     torch.distributed.destroy_process_group() and at interpreter exit (see _hook_teardown)."""
@@ -507,7 +510,8 @@ def release_all_graphs() -> None:
         g.release()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
-    release_peer_arenas()
+    if peer_arenas:
+        release_peer_arenas()
 
 
 def _hook_teardown() -> None:
@@ -517,7 +521,7 @@ def _hook_teardown() -> None:
     _TEARDOWN_HOOKED = True
     import atexit
     import functools
-    atexit.register(release_all_graphs)
+    atexit.register(release_all_graphs, False)      # at exit the driver reclaims the peer arenas; no collective there
     orig = dist.destroy_process_group
 
     @functools.wraps(orig)
