@@ -215,20 +215,39 @@ class PeerExchange:
                                                   dst_row_stride, rows, row_bytes, channel, self.rank, self.P, _ops._stream_ptr()))
         self.exchanges += 1
 
+    @staticmethod
+    def plan_rows_to_cols(R: int, Cc: int, d: int, P: int, rank: int, itemsize: int = 4):
+        """af2_peer_exchange arguments (bytes) that turn [R, Cc, d] row shards into [P*R, Cc/P, d] column shards:
+        chunk p = my R rows x the Cc/P columns of rank p; it lands in rank p's column buffer at rows rank*R.. (contiguous).
+        dst_off is relative to the destination buffer.  Pure arithmetic (tests/test_parallel_schedule.py emulates it)."""
+        chunk = Cc // P * d * itemsize
+        return dict(src_peer_stride=chunk, src_row_stride=Cc * d * itemsize, dst_off=rank * R * chunk, dst_row_stride=chunk,
+                    rows=R, row_bytes=chunk)
+
+    @staticmethod
+    def plan_cols_to_rows(RR: int, Cl: int, d: int, P: int, rank: int, itemsize: int = 4):
+        """The way back: [P*R, Cl, d] column shards -> [R, P*Cl, d] row shards.  Chunk p = the R rows of rank p x my Cl
+        columns (contiguous at the source); it lands in rank p's row buffer at columns rank*Cl.. of every row."""
+        R, chunk = RR // P, Cl * d * itemsize
+        return dict(src_peer_stride=R * chunk, src_row_stride=chunk, dst_off=rank * chunk, dst_row_stride=P * chunk,
+                    rows=R, row_bytes=chunk)
+
+    def _run(self, src: torch.Tensor, plan: dict, dst_buffer_off: int, channel: int):
+        self._exchange(src, plan["src_peer_stride"], plan["src_row_stride"], dst_buffer_off + plan["dst_off"], plan["dst_row_stride"],
+                       plan["rows"], plan["row_bytes"], channel)
+
     def rows_to_cols(self, t_row: torch.Tensor, track: int, channel: int = 0) -> torch.Tensor:
         """[R, C, d] (my rows, all columns; the track's row buffer) -> the track's column buffer [P*R, C/P, d]."""
         R, Cc, d = t_row.shape
-        chunk = Cc // self.P * d * 4
         assert t_row.data_ptr() == self.base + self.off[(track, "row")] and tuple(t_row.shape) == self.shapes[(track, "row")]
-        self._exchange(t_row, chunk, Cc * d * 4, self.off[(track, "col")] + self.rank * R * chunk, chunk, R, chunk, channel)
+        self._run(t_row, self.plan_rows_to_cols(R, Cc, d, self.P, self.rank), self.off[(track, "col")], channel)
         return self.buffer(track, "col")
 
     def cols_to_rows(self, t_col: torch.Tensor, track: int, channel: int = 0) -> torch.Tensor:
         """[P*R, Cl, d] (all rows, my columns; the track's column buffer) -> the track's row buffer [R, P*Cl, d]."""
         RR, Cl, d = t_col.shape
-        R, chunk = RR // self.P, Cl * d * 4
         assert t_col.data_ptr() == self.base + self.off[(track, "col")] and tuple(t_col.shape) == self.shapes[(track, "col")]
-        self._exchange(t_col, R * chunk, chunk, self.off[(track, "row")] + self.rank * chunk, self.P * chunk, R, chunk, channel)
+        self._run(t_col, self.plan_cols_to_rows(RR, Cl, d, self.P, self.rank), self.off[(track, "row")], channel)
         return self.buffer(track, "row")
 
     def error(self) -> bool:

@@ -94,3 +94,43 @@ def test_merge_gathered_pieces_drops_alignment_padding():
     wide = torch.zeros(8 * 2, 3, 64)
     same, n_pieces = CudaStageOps._merge_mn_pieces(wide, 8, 2, 512)          # >= 64 columns per piece: addressed in place
     assert same is wide and n_pieces == 8
+
+
+def _emulate_peer_exchange(src_bytes, plans, dst_nbytes):
+    """What csrc/peer_api.inl's kernel does with the arguments of PeerExchange.plan_*: rank r copies, for every peer p,
+    `rows` rows of `row_bytes` from src[r] + p*src_peer_stride + row*src_row_stride to dst[p] + dst_off + row*dst_row_stride."""
+    import numpy as np
+    P = len(src_bytes)
+    dst = [np.zeros(dst_nbytes, dtype=np.uint8) for _ in range(P)]
+    for r in range(P):
+        pl = plans[r]
+        for p in range(P):
+            for row in range(pl["rows"]):
+                so = p * pl["src_peer_stride"] + row * pl["src_row_stride"]
+                do = pl["dst_off"] + row * pl["dst_row_stride"]
+                dst[p][do:do + pl["row_bytes"]] = src_bytes[r][so:so + pl["row_bytes"]]
+    return dst
+
+
+def test_peer_exchange_plans_are_the_all_to_all_layouts():
+    """Host arithmetic of the peer-store exchange (no GPU): emulating the kernel's copies with the planned strides and
+    offsets on P simulated ranks gives exactly the column shards / row shards of the full tensor."""
+    import numpy as np
+    import torch
+
+    from alphafold2_b200.parallel import PeerExchange
+    for (N, C, d, P) in [(8, 8, 4, 2), (16, 16, 4, 4), (24, 24, 8, 8), (6, 12, 4, 2)]:
+        full = torch.arange(N * C * d, dtype=torch.float32).view(N, C, d)
+        R, Cl = N // P, C // P
+        rows = [full[r * R:(r + 1) * R].contiguous() for r in range(P)]                       # [R, C, d]
+        cols = [full[:, r * Cl:(r + 1) * Cl].contiguous() for r in range(P)]                  # [N, Cl, d]
+        nbytes = R * C * d * 4
+        as_bytes = lambda t: np.frombuffer(t.numpy().tobytes(), dtype=np.uint8)              # noqa: E731
+        plans = [PeerExchange.plan_rows_to_cols(R, C, d, P, r) for r in range(P)]
+        got = _emulate_peer_exchange([as_bytes(t) for t in rows], plans, nbytes)
+        for r in range(P):
+            assert np.array_equal(got[r], as_bytes(cols[r])), ("rows_to_cols", N, C, d, P, r)
+        plans = [PeerExchange.plan_cols_to_rows(N, Cl, d, P, r) for r in range(P)]
+        back = _emulate_peer_exchange(got, plans, nbytes)
+        for r in range(P):
+            assert np.array_equal(back[r], as_bytes(rows[r])), ("cols_to_rows", N, C, d, P, r)
